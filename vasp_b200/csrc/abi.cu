@@ -1,0 +1,620 @@
+// extern "C" surface of libvasp_hemo.so (include/vasp_hemo.h): handle lifetime, double-buffered snapshot staging,
+// result export and the dlopen'ed NCCL reduction.  No torch, no CPU compute path: every numeric result comes from the
+// kernels in k0_precompute.cu / k2_traction.cu.
+#include <dlfcn.h>
+#include <nccl.h>  // types only; the library is resolved at run time
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void vh_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+} g_nccl;
+
+int nccl_load() {
+    if (g_nccl.lib) return VH_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    VH_CHECK(g_nccl.lib, VH_ERR_NCCL, "NCCL not found: %s", dlerror());
+#define VH_SYM(field, name)                                                          \
+    *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, name);                              \
+    VH_CHECK(g_nccl.field, VH_ERR_NCCL, "NCCL symbol %s missing", name)
+    VH_SYM(GetUniqueId, "ncclGetUniqueId");
+    VH_SYM(CommInitRank, "ncclCommInitRank");
+    VH_SYM(AllReduce, "ncclAllReduce");
+    VH_SYM(CommDestroy, "ncclCommDestroy");
+    VH_SYM(GetErrorString, "ncclGetErrorString");
+#undef VH_SYM
+    return VH_OK;
+}
+
+#define VH_NCCL(call)                                                                                    \
+    do {                                                                                                 \
+        ncclResult_t r__ = (call);                                                                       \
+        if (r__ != ncclSuccess) {                                                                        \
+            vh_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r__));      \
+            return VH_ERR_NCCL;                                                                          \
+        }                                                                                                \
+    } while (0)
+
+int ensure_run_buffers(vh_handle* h) {
+    const int64_t nF = h->nF;
+    if (!h->d_sums) {
+        VH_CUDA(cudaMalloc(&h->d_sums, sizeof(double) * VH_NSUM * nF));
+        VH_CUDA(cudaMalloc(&h->d_tau_last[0], sizeof(double) * 9 * nF));
+        VH_CUDA(cudaMalloc(&h->d_tau_last[1], sizeof(double) * 9 * nF));
+    }
+    return VH_OK;
+}
+
+int check_ready(vh_handle* h, const char* who) {
+    VH_CHECK(h, VH_ERR_ARG, "%s: null handle", who);
+    VH_CUDA(cudaSetDevice(h->device));
+    VH_CHECK(h->nF > 0, VH_ERR_ARG, "%s: call vh_set_mesh first", who);
+    VH_CHECK(h->order != 0, VH_ERR_ARG, "%s: call vh_set_velocity_layout first", who);
+    VH_CHECK(h->begun, VH_ERR_ARG, "%s: call vh_begin first", who);
+    return VH_OK;
+}
+
+__global__ void k_flush(double* __restrict__ p, int64_t n, double v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += step) p[i] = v;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vh_last_error(void) { return g_err; }
+
+int vh_device_count(int* n) {
+    VH_CUDA(cudaGetDeviceCount(n));
+    return VH_OK;
+}
+
+int vh_create(int device, vh_handle** out) {
+    VH_CHECK(out, VH_ERR_ARG, "vh_create: null out");
+    int ndev = 0;
+    VH_CUDA(cudaGetDeviceCount(&ndev));
+    VH_CHECK(ndev > 0, VH_ERR_CUDA, "vh_create: no CUDA device visible (this library has no CPU path)");
+    VH_CHECK(device >= 0 && device < ndev, VH_ERR_ARG, "vh_create: device %d out of range [0,%d)", device, ndev);
+    VH_CUDA(cudaSetDevice(device));
+    vh_handle* h = new vh_handle();
+    h->device = device;
+    cudaDeviceProp prop;
+    VH_CUDA(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    VH_CUDA(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+    VH_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        VH_CUDA(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+        VH_CUDA(cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming));
+        VH_CUDA(cudaEventCreateWithFlags(&h->ev_wss[i], cudaEventDisableTiming));
+    }
+    VH_CUDA(cudaEventCreate(&h->ev_t0));
+    VH_CUDA(cudaEventCreate(&h->ev_t1));
+    VH_CUDA(cudaEventCreate(&h->ev_k0));
+    VH_CUDA(cudaEventCreate(&h->ev_k1));
+    *out = h;
+    return VH_OK;
+}
+
+int vh_destroy(vh_handle* h) {
+    if (!h) return VH_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    vh_nccl_destroy(h);
+    k_free_run_buffers(h);
+    void* ptrs[] = {h->d_xyz, h->d_tets, h->d_facet_cell, h->d_facet_verts, h->d_bcell_parent, h->d_btopology,
+                    h->d_bvert_parent, h->d_facet_local, h->d_bcell_local, h->d_blocal_soa, h->d_glam, h->d_normal,
+                    h->d_area, h->d_work, h->d_m_lf, h->d_m_w, h->d_facet_nodes, h->d_slot, h->d_flush, h->d_scalar};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(h->ev_copied[i]);
+        cudaEventDestroy(h->ev_consumed[i]);
+        cudaEventDestroy(h->ev_wss[i]);
+    }
+    cudaEventDestroy(h->ev_t0);
+    cudaEventDestroy(h->ev_t1);
+    cudaEventDestroy(h->ev_k0);
+    cudaEventDestroy(h->ev_k1);
+    cudaStreamDestroy(h->s_compute);
+    cudaStreamDestroy(h->s_copy);
+    delete h;
+    return VH_OK;
+}
+
+int vh_set_mesh(vh_handle* h, const double* xyz, int64_t nv, const int64_t* tets, int64_t nc) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_set_mesh: null handle");
+    VH_CUDA(cudaSetDevice(h->device));
+    return k0_build_mesh(h, xyz, nv, tets, nc);
+}
+
+int vh_set_velocity_layout(vh_handle* h, int order, const double* refined_xyz, int64_t n_nodes, double tol,
+                           const int64_t* node_perm, const int64_t comp_offset[3], int64_t node_stride) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_set_velocity_layout: null handle");
+    VH_CUDA(cudaSetDevice(h->device));
+    VH_CHECK(comp_offset && node_stride >= 1, VH_ERR_ARG, "vh_set_velocity_layout: bad layout");
+    int64_t max_slot = (n_nodes - 1) * node_stride;
+    for (int c = 0; c < 3; ++c) VH_CHECK(comp_offset[c] >= 0, VH_ERR_ARG, "negative component offset");
+    VH_CHECK(max_slot < (1LL << 31), VH_ERR_ARG, "velocity vector too long for int32 gather slots");
+    h->node_stride = node_stride;
+    for (int c = 0; c < 3; ++c) h->comp_offset[c] = comp_offset[c];
+    int64_t top = comp_offset[0];
+    for (int c = 1; c < 3; ++c) top = comp_offset[c] > top ? comp_offset[c] : top;
+    h->vec_len = top + max_slot + 1;  // doubles per snapshot vector that the gather can touch
+    k_free_run_buffers(h);
+    return k0_build_velocity_map(h, order, refined_xyz, n_nodes, tol, node_perm);
+}
+
+int vh_get_sizes(vh_handle* h, int64_t n[6]) {
+    VH_CHECK(h && n, VH_ERR_ARG, "vh_get_sizes: null argument");
+    n[0] = h->nF; n[1] = h->nBV; n[2] = h->nW; n[3] = h->nMulti; n[4] = h->ndof; n[5] = h->n_nodes;
+    return VH_OK;
+}
+
+int vh_get_maps(vh_handle* h, int32_t* facet_cell, int8_t* facet_local, int32_t* facet_verts, int32_t* bcell_parent,
+                int32_t* btopology, int32_t* bvert_parent, int8_t* bcell_local, int32_t* facet_nodes) {
+    VH_CHECK(h && h->nF > 0, VH_ERR_ARG, "vh_get_maps: call vh_set_mesh first");
+    VH_CUDA(cudaSetDevice(h->device));
+    const int64_t nF = h->nF;
+#define VH_D2H(dst, src, bytes) \
+    if (dst) VH_CUDA(cudaMemcpy(dst, src, (size_t)(bytes), cudaMemcpyDeviceToHost))
+    VH_D2H(facet_cell, h->d_facet_cell, 4 * nF);
+    VH_D2H(facet_local, h->d_facet_local, nF);
+    VH_D2H(facet_verts, h->d_facet_verts, 12 * nF);
+    VH_D2H(bcell_parent, h->d_bcell_parent, 12 * nF);
+    VH_D2H(btopology, h->d_btopology, 12 * nF);
+    VH_D2H(bvert_parent, h->d_bvert_parent, 4 * h->nBV);
+    VH_D2H(bcell_local, h->d_bcell_local, 3 * nF);
+    if (facet_nodes) {
+        VH_CHECK(h->order != 0, VH_ERR_ARG, "vh_get_maps: facet_nodes needs vh_set_velocity_layout");
+        // device layout is [ndof][nF]; export as [nF][ndof]
+        std::vector<int32_t> tmp((size_t)h->ndof * nF);
+        VH_CUDA(cudaMemcpy(tmp.data(), h->d_facet_nodes, sizeof(int32_t) * tmp.size(), cudaMemcpyDeviceToHost));
+        for (int64_t f = 0; f < nF; ++f)
+            for (int k = 0; k < h->ndof; ++k) facet_nodes[f * h->ndof + k] = tmp[(size_t)k * nF + f];
+    }
+    return VH_OK;
+}
+
+int vh_get_geometry(vh_handle* h, double* normal, double* area, double* glam) {
+    VH_CHECK(h && h->nF > 0, VH_ERR_ARG, "vh_get_geometry: call vh_set_mesh first");
+    VH_CUDA(cudaSetDevice(h->device));
+    const int64_t nF = h->nF;
+    VH_D2H(area, h->d_area, 8 * nF);
+    auto export_rows = [&](double* dst, const double* d_src, int rows) -> int {
+        std::vector<double> tmp((size_t)rows * nF);
+        VH_CUDA(cudaMemcpy(tmp.data(), d_src, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
+        for (int64_t f = 0; f < nF; ++f)
+            for (int r = 0; r < rows; ++r) dst[f * rows + r] = tmp[(size_t)r * nF + f];
+        return VH_OK;
+    };
+    if (normal) VH_TRY(export_rows(normal, h->d_normal, 3));
+    if (glam) VH_TRY(export_rows(glam, h->d_glam, 12));
+    return VH_OK;
+}
+#undef VH_D2H
+
+int vh_begin(vh_handle* h, double mu, double dt) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_begin: null handle");
+    VH_CUDA(cudaSetDevice(h->device));
+    VH_CHECK(h->nF > 0 && h->order != 0, VH_ERR_ARG, "vh_begin: set mesh and velocity layout first");
+    VH_CHECK(dt != 0.0, VH_ERR_ARG, "vh_begin: dt must be non-zero");
+    VH_TRY(ensure_run_buffers(h));
+    h->mu = mu;
+    h->dt = dt;
+    h->count = 0;
+    h->have_tau_last = false;
+    h->kernel_ms = h->h2d_ms = 0.0;
+    VH_CUDA(cudaMemsetAsync(h->d_sums, 0, sizeof(double) * VH_NSUM * h->nF, h->s_compute));
+    VH_CUDA(cudaMemsetAsync(h->d_tau_last[0], 0, sizeof(double) * 9 * h->nF, h->s_compute));
+    VH_CUDA(cudaMemsetAsync(h->d_tau_last[1], 0, sizeof(double) * 9 * h->nF, h->s_compute));
+    VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    h->begun = true;
+    return VH_OK;
+}
+
+int vh_set_tuning(vh_handle* h, int64_t batch_snapshots, int64_t chunk_snapshots) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_set_tuning: null handle");
+    VH_CHECK(batch_snapshots >= 0 && chunk_snapshots >= 0, VH_ERR_ARG, "vh_set_tuning: negative value");
+    if (batch_snapshots != h->batch_snapshots) {
+        for (int i = 0; i < 2; ++i) {
+            if (h->d_stage[i]) cudaFree(h->d_stage[i]);
+            if (h->d_wss_stage[i]) cudaFree(h->d_wss_stage[i]);
+            h->d_stage[i] = h->d_wss_stage[i] = nullptr;
+        }
+        h->stage_cap = h->wss_stage_cap = 0;
+    }
+    h->batch_snapshots = batch_snapshots;
+    h->chunk_snapshots = chunk_snapshots;
+    return VH_OK;
+}
+
+static int prev_mode_for(vh_handle* h, int flags, const char* who, int* mode) {
+    if (flags & VH_PUSH_HALO_FIRST) {
+        *mode = 2;
+    } else if (flags & VH_PUSH_GLOBAL_FIRST) {
+        *mode = 0;
+    } else {
+        VH_CHECK(h->have_tau_last, VH_ERR_ARG,
+                 "%s: first push of a time loop needs VH_PUSH_GLOBAL_FIRST or VH_PUSH_HALO_FIRST", who);
+        *mode = 1;
+    }
+    return VH_OK;
+}
+
+int vh_push_snapshots_device(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_bytes, int flags,
+                             double* d_wss_out) {
+    VH_TRY(check_ready(h, "vh_push_snapshots_device"));
+    VH_CHECK(d_u && n_snap > 0, VH_ERR_ARG, "vh_push_snapshots_device: nothing to push");
+    VH_CHECK(stride_bytes % 8 == 0 && stride_bytes >= 8 * h->vec_len, VH_ERR_ARG,
+             "vh_push_snapshots_device: stride %lld smaller than a vector (%lld doubles)", (long long)stride_bytes,
+             (long long)h->vec_len);
+    int mode = 0;
+    VH_TRY(prev_mode_for(h, flags, "vh_push_snapshots_device", &mode));
+    const int64_t stride = stride_bytes / 8;
+    if (mode == 2) {
+        VH_CHECK(n_snap >= 2, VH_ERR_ARG, "halo push needs at least one real snapshot after the halo");
+        return k2_launch(h, d_u + stride, n_snap - 1, stride, 2, d_wss_out);
+    }
+    return k2_launch(h, d_u, n_snap, stride, mode, d_wss_out);
+}
+
+int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t stride_bytes, int flags, double* wss_out) {
+    VH_TRY(check_ready(h, "vh_push_snapshots"));
+    VH_CHECK(u && n_snap > 0, VH_ERR_ARG, "vh_push_snapshots: nothing to push");
+    const int64_t vec_bytes = 8 * h->vec_len;
+    VH_CHECK(stride_bytes % 8 == 0 && stride_bytes >= vec_bytes, VH_ERR_ARG,
+             "vh_push_snapshots: stride %lld smaller than a vector (%lld bytes)", (long long)stride_bytes,
+             (long long)vec_bytes);
+    int mode = 0;
+    VH_TRY(prev_mode_for(h, flags, "vh_push_snapshots", &mode));
+    const bool halo = mode == 2;
+    VH_CHECK(!halo || n_snap >= 2, VH_ERR_ARG, "halo push needs at least one real snapshot after the halo");
+    const int64_t nF = h->nF;
+
+    // stage capacity: user value, else as many snapshots as fit in ~30 % of free memory / 2 buffers, capped at 8 GiB
+    if (h->stage_cap == 0) {
+        int64_t cap = h->batch_snapshots;
+        if (cap <= 0) {
+            size_t free_b = 0, total_b = 0;
+            VH_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            int64_t per_snap = vec_bytes + (wss_out ? 72 * nF : 0);
+            int64_t budget = (int64_t)(0.3 * (double)free_b) / 2;
+            if (budget > (8LL << 30)) budget = 8LL << 30;
+            cap = budget / per_snap;
+            if (cap > n_snap) cap = n_snap;
+        }
+        if (cap < 2) cap = 2;
+        for (int i = 0; i < 2; ++i) VH_CUDA(cudaMalloc(&h->d_stage[i], (size_t)(cap * vec_bytes)));
+        h->stage_cap = cap;
+    }
+    if (wss_out && h->wss_stage_cap < h->stage_cap) {
+        for (int i = 0; i < 2; ++i) {
+            if (h->d_wss_stage[i]) cudaFree(h->d_wss_stage[i]);
+            VH_CUDA(cudaMalloc(&h->d_wss_stage[i], (size_t)(h->stage_cap * 72 * nF)));
+        }
+        h->wss_stage_cap = h->stage_cap;
+    }
+
+    std::vector<cudaEvent_t> evs;  // (h2d start, h2d stop, kernel start, kernel stop) per batch
+    auto new_event = [&](cudaEvent_t* e) -> int {
+        VH_CUDA(cudaEventCreate(e));
+        evs.push_back(*e);
+        return VH_OK;
+    };
+    int64_t pos = 0, real_done = 0;
+    int b = 0;
+    bool first = true;
+    int rc = VH_OK;
+    while (pos < n_snap && rc == VH_OK) {
+        const int buf = b & 1;
+        int64_t nb = n_snap - pos;
+        if (nb > h->stage_cap) nb = h->stage_cap;
+        cudaEvent_t c0, c1, k0, k1;
+        if ((rc = new_event(&c0)) || (rc = new_event(&c1)) || (rc = new_event(&k0)) || (rc = new_event(&k1))) break;
+        // copy stream: wait until the kernel that last read this buffer is done, then H2D
+        cudaStreamWaitEvent(h->s_copy, h->ev_consumed[buf], 0);
+        cudaEventRecord(c0, h->s_copy);
+        cudaError_t ce = cudaMemcpy2DAsync(h->d_stage[buf], (size_t)vec_bytes, (const char*)u + pos * stride_bytes,
+                                           (size_t)stride_bytes, (size_t)vec_bytes, (size_t)nb, cudaMemcpyHostToDevice,
+                                           h->s_copy);
+        if (ce != cudaSuccess) {
+            vh_set_error("vh_push_snapshots: H2D copy failed: %s", cudaGetErrorString(ce));
+            rc = VH_ERR_CUDA;
+            break;
+        }
+        cudaEventRecord(c1, h->s_copy);
+        cudaEventRecord(h->ev_copied[buf], h->s_copy);
+        // compute stream
+        cudaStreamWaitEvent(h->s_compute, h->ev_copied[buf], 0);
+        if (wss_out) cudaStreamWaitEvent(h->s_compute, h->ev_wss[buf], 0);  // previous D2H of this wss buffer done
+        const double* d_u = h->d_stage[buf];
+        int64_t n_real = nb;
+        int pm = first ? mode : 1;
+        if (first && halo) {
+            d_u += h->vec_len;
+            n_real = nb - 1;
+        }
+        cudaEventRecord(k0, h->s_compute);
+        rc = k2_launch(h, d_u, n_real, h->vec_len, pm, wss_out ? h->d_wss_stage[buf] : nullptr);
+        cudaEventRecord(k1, h->s_compute);
+        cudaEventRecord(h->ev_consumed[buf], h->s_compute);
+        if (rc == VH_OK && wss_out && n_real > 0) {
+            cudaStreamWaitEvent(h->s_copy, h->ev_consumed[buf], 0);
+            ce = cudaMemcpyAsync(wss_out + real_done * 9 * nF, h->d_wss_stage[buf], (size_t)(n_real * 72 * nF),
+                                 cudaMemcpyDeviceToHost, h->s_copy);
+            if (ce != cudaSuccess) {
+                vh_set_error("vh_push_snapshots: D2H copy failed: %s", cudaGetErrorString(ce));
+                rc = VH_ERR_CUDA;
+            }
+            cudaEventRecord(h->ev_wss[buf], h->s_copy);
+        }
+        real_done += n_real;
+        pos += nb;
+        first = false;
+        ++b;
+    }
+    cudaError_t e1 = cudaStreamSynchronize(h->s_copy), e2 = cudaStreamSynchronize(h->s_compute);
+    if (rc == VH_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+        vh_set_error("vh_push_snapshots: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        rc = VH_ERR_CUDA;
+    }
+    for (size_t i = 0; i + 3 < evs.size() && rc == VH_OK; i += 4) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, evs[i], evs[i + 1]) == cudaSuccess) h->h2d_ms += ms;
+        if (cudaEventElapsedTime(&ms, evs[i + 2], evs[i + 3]) == cudaSuccess) h->kernel_ms += ms;
+    }
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    return rc;
+}
+
+int vh_get_sums(vh_handle* h, double* sums, int64_t* count) {
+    VH_TRY(check_ready(h, "vh_get_sums"));
+    VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    if (sums) VH_CUDA(cudaMemcpy(sums, h->d_sums, sizeof(double) * VH_NSUM * h->nF, cudaMemcpyDeviceToHost));
+    if (count) *count = h->count;
+    return VH_OK;
+}
+
+int vh_set_sums(vh_handle* h, const double* sums, int64_t count) {
+    VH_TRY(check_ready(h, "vh_set_sums"));
+    VH_CHECK(sums, VH_ERR_ARG, "vh_set_sums: null sums");
+    VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    VH_CUDA(cudaMemcpy(h->d_sums, sums, sizeof(double) * VH_NSUM * h->nF, cudaMemcpyHostToDevice));
+    h->count = count;
+    return VH_OK;
+}
+
+int vh_sums_device_ptr(vh_handle* h, double** d_sums) {
+    VH_TRY(check_ready(h, "vh_sums_device_ptr"));
+    *d_sums = h->d_sums;
+    return VH_OK;
+}
+
+int vh_get_tau_last(vh_handle* h, double* tau) {
+    VH_TRY(check_ready(h, "vh_get_tau_last"));
+    VH_CHECK(tau, VH_ERR_ARG, "vh_get_tau_last: null output");
+    VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    const int64_t nF = h->nF;
+    std::vector<double> tmp((size_t)9 * nF);
+    VH_CUDA(cudaMemcpy(tmp.data(), h->d_tau_last[h->tau_cur], sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
+    for (int64_t f = 0; f < nF; ++f)
+        for (int r = 0; r < 9; ++r) tau[f * 9 + r] = tmp[(size_t)r * nF + f];
+    return VH_OK;
+}
+
+int vh_finalize(vh_handle* h, int64_t n_total, double* tawss, double* osi, double* rrt, double* ecap, double* twssg) {
+    VH_TRY(check_ready(h, "vh_finalize"));
+    VH_CHECK(n_total > 0, VH_ERR_ARG, "vh_finalize: n_total must be positive");
+    const int64_t n3 = 3 * h->nF;
+    double* d_out = nullptr;
+    VH_CUDA(cudaMalloc(&d_out, sizeof(double) * 5 * n3));
+    int rc = k4_finalize(h, n_total, d_out);
+    double* outs[5] = {tawss, osi, rrt, ecap, twssg};
+    for (int i = 0; i < 5 && rc == VH_OK; ++i) {
+        if (!outs[i]) continue;
+        cudaError_t e = cudaMemcpyAsync(outs[i], d_out + i * n3, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->s_compute);
+        if (e != cudaSuccess) {
+            vh_set_error("vh_finalize: D2H failed: %s", cudaGetErrorString(e));
+            rc = VH_ERR_CUDA;
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(h->s_compute);
+    cudaFree(d_out);
+    if (rc == VH_OK && e != cudaSuccess) {
+        vh_set_error("vh_finalize: %s", cudaGetErrorString(e));
+        rc = VH_ERR_CUDA;
+    }
+    return rc;
+}
+
+int vh_sync(vh_handle* h) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_sync: null handle");
+    VH_CUDA(cudaSetDevice(h->device));
+    VH_CUDA(cudaStreamSynchronize(h->s_copy));
+    VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    return VH_OK;
+}
+
+int vh_get_timers(vh_handle* h, double* kernel_ms, double* h2d_ms, int64_t* launches) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_get_timers: null handle");
+    if (kernel_ms) *kernel_ms = h->kernel_ms;
+    if (h2d_ms) *h2d_ms = h->h2d_ms;
+    if (launches) *launches = h->launches;
+    return VH_OK;
+}
+
+int vh_timer_start(vh_handle* h) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_timer_start: null handle");
+    VH_CUDA(cudaSetDevice(h->device));
+    VH_CUDA(cudaEventRecord(h->ev_t0, h->s_compute));
+    return VH_OK;
+}
+
+int vh_timer_stop(vh_handle* h, double* ms) {
+    VH_CHECK(h && ms, VH_ERR_ARG, "vh_timer_stop: null argument");
+    VH_CUDA(cudaSetDevice(h->device));
+    VH_CUDA(cudaEventRecord(h->ev_t1, h->s_compute));
+    VH_CUDA(cudaEventSynchronize(h->ev_t1));
+    float f = 0.f;
+    VH_CUDA(cudaEventElapsedTime(&f, h->ev_t0, h->ev_t1));
+    *ms = f;
+    return VH_OK;
+}
+
+int vh_alloc_pinned(void** p, int64_t nbytes) {
+    VH_CHECK(p && nbytes > 0, VH_ERR_ARG, "vh_alloc_pinned: bad argument");
+    VH_CUDA(cudaHostAlloc(p, (size_t)nbytes, cudaHostAllocDefault));
+    return VH_OK;
+}
+
+int vh_free_pinned(void* p) {
+    if (p) VH_CUDA(cudaFreeHost(p));
+    return VH_OK;
+}
+
+int vh_alloc_device(vh_handle* h, void** d_p, int64_t nbytes) {
+    VH_CHECK(h && d_p && nbytes > 0, VH_ERR_ARG, "vh_alloc_device: bad argument");
+    VH_CUDA(cudaSetDevice(h->device));
+    VH_CUDA(cudaMalloc(d_p, (size_t)nbytes));
+    return VH_OK;
+}
+
+int vh_free_device(vh_handle* h, void* d_p) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_free_device: null handle");
+    VH_CUDA(cudaSetDevice(h->device));
+    if (d_p) VH_CUDA(cudaFree(d_p));
+    return VH_OK;
+}
+
+int vh_memcpy_h2d(vh_handle* h, void* d_dst, const void* src, int64_t nbytes) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_memcpy_h2d: null handle");
+    VH_CUDA(cudaSetDevice(h->device));
+    VH_CUDA(cudaMemcpyAsync(d_dst, src, (size_t)nbytes, cudaMemcpyHostToDevice, h->s_compute));
+    VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    return VH_OK;
+}
+
+int vh_memcpy_d2h(vh_handle* h, void* dst, const void* d_src, int64_t nbytes) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_memcpy_d2h: null handle");
+    VH_CUDA(cudaSetDevice(h->device));
+    VH_CUDA(cudaMemcpyAsync(dst, d_src, (size_t)nbytes, cudaMemcpyDeviceToHost, h->s_compute));
+    VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    return VH_OK;
+}
+
+int vh_flush_l2(vh_handle* h) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_flush_l2: null handle");
+    VH_CUDA(cudaSetDevice(h->device));
+    if (!h->d_flush) {
+        h->flush_bytes = 512LL << 20;  // 4x the 126 MB L2
+        VH_CUDA(cudaMalloc(&h->d_flush, (size_t)h->flush_bytes));
+    }
+    static double tick = 0.0;
+    tick += 1.0;
+    k_flush<<<h->sm_count * 8, 256, 0, h->s_compute>>>((double*)h->d_flush, h->flush_bytes / 8, tick);
+    VH_CUDA(cudaGetLastError());
+    return VH_OK;
+}
+
+int vh_mem_info(vh_handle* h, int64_t* free_bytes, int64_t* total_bytes) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_mem_info: null handle");
+    VH_CUDA(cudaSetDevice(h->device));
+    size_t f = 0, t = 0;
+    VH_CUDA(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+    return VH_OK;
+}
+
+// ---- NCCL ---------------------------------------------------------------------------------------------------------
+int vh_nccl_unique_id(char id[128]) {
+    VH_TRY(nccl_load());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId uid;
+    VH_NCCL(g_nccl.GetUniqueId(&uid));
+    memcpy(id, &uid, 128);
+    return VH_OK;
+}
+
+int vh_nccl_init(vh_handle* h, const char id[128], int rank, int world) {
+    VH_CHECK(h && id, VH_ERR_ARG, "vh_nccl_init: null argument");
+    VH_CHECK(world >= 1 && rank >= 0 && rank < world, VH_ERR_ARG, "vh_nccl_init: bad rank/world %d/%d", rank, world);
+    VH_TRY(nccl_load());
+    VH_CUDA(cudaSetDevice(h->device));
+    vh_nccl_destroy(h);
+    ncclUniqueId uid;
+    memcpy(&uid, id, 128);
+    ncclComm_t comm;
+    VH_NCCL(g_nccl.CommInitRank(&comm, world, uid, rank));
+    h->nccl_comm = comm;
+    h->rank = rank;
+    h->world = world;
+    if (!h->d_scalar) VH_CUDA(cudaMalloc(&h->d_scalar, sizeof(double) * 2));
+    return VH_OK;
+}
+
+int vh_nccl_allreduce_sums(vh_handle* h) {
+    VH_TRY(check_ready(h, "vh_nccl_allreduce_sums"));
+    VH_CHECK(h->nccl_comm, VH_ERR_NCCL, "vh_nccl_allreduce_sums: call vh_nccl_init first");
+    double cnt = (double)h->count;
+    VH_CUDA(cudaMemcpyAsync(h->d_scalar, &cnt, sizeof(double), cudaMemcpyHostToDevice, h->s_compute));
+    VH_NCCL(g_nccl.AllReduce(h->d_sums, h->d_sums, (size_t)(VH_NSUM * h->nF), ncclDouble, ncclSum,
+                             (ncclComm_t)h->nccl_comm, h->s_compute));
+    VH_NCCL(g_nccl.AllReduce(h->d_scalar, h->d_scalar, 1, ncclDouble, ncclSum, (ncclComm_t)h->nccl_comm, h->s_compute));
+    VH_CUDA(cudaMemcpyAsync(&cnt, h->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, h->s_compute));
+    VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    h->count = (int64_t)(cnt + 0.5);
+    return VH_OK;
+}
+
+int vh_nccl_allreduce_max(vh_handle* h, double* value) {
+    VH_CHECK(h && value, VH_ERR_ARG, "vh_nccl_allreduce_max: null argument");
+    VH_CHECK(h->nccl_comm, VH_ERR_NCCL, "vh_nccl_allreduce_max: call vh_nccl_init first");
+    VH_CUDA(cudaSetDevice(h->device));
+    VH_CUDA(cudaMemcpyAsync(h->d_scalar, value, sizeof(double), cudaMemcpyHostToDevice, h->s_compute));
+    VH_NCCL(g_nccl.AllReduce(h->d_scalar, h->d_scalar, 1, ncclDouble, ncclMax, (ncclComm_t)h->nccl_comm, h->s_compute));
+    VH_CUDA(cudaMemcpyAsync(value, h->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, h->s_compute));
+    VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    return VH_OK;
+}
+
+int vh_nccl_barrier(vh_handle* h) {
+    double v = 0.0;
+    return vh_nccl_allreduce_max(h, &v);
+}
+
+int vh_nccl_destroy(vh_handle* h) {
+    if (h && h->nccl_comm && g_nccl.CommDestroy) {
+        g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
+        h->nccl_comm = nullptr;
+    }
+    return VH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+// Shared declarations of libvasp_hemo.so (sm_100a only).  See include/vasp_hemo.h for the ABI and DESIGN.md for
+// the data layout.  Reference path: src/vasp/postprocessing/postprocessing_fenics/compute_hemodynamics.py.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/vasp_hemo.h"
+
+// ---- error plumbing -------------------------------------------------------------------------------------------
+void vh_set_error(const char* fmt, ...);
+
+#define VH_CUDA(call)                                                                                     \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess) {                                                                         \
+            vh_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));          \
+            return VH_ERR_CUDA;                                                                           \
+        }                                                                                                 \
+    } while (0)
+
+#define VH_CHECK(cond, code, ...)                                                                         \
+    do {                                                                                                  \
+        if (!(cond)) {                                                                                    \
+            vh_set_error(__VA_ARGS__);                                                                    \
+            return (code);                                                                                \
+        }                                                                                                 \
+    } while (0)
+
+#define VH_TRY(expr)                                                                                      \
+    do {                                                                                                  \
+        int rc__ = (expr);                                                                                \
+        if (rc__ != VH_OK) return rc__;                                                                   \
+    } while (0)
+
+// Number of running sums per facet: 9 (sum tau) + 3 (sum |tau|) + 3 (sum P(|dtau/dt|)); SoA rows of length nF.
+constexpr int VH_NSUM = 15;
+constexpr int VH_MAX_CONTRIB = 4;  // a tet has at most 4 exterior facets
+
+// Per-facet constants in HBM, all SoA over facets (row r of an array with R rows: ptr[r * nF + f]).
+struct FacetTables {
+    int64_t nF;
+    const int32_t* slot;   // [ndof][nF]  node_stride * node_perm[velocity node of cell dof k]
+    const double* glam;    // [12][nF]    grad lambda_a (a-major, xyz minor), a in facet-canonical labels
+    const double* normal;  // [3][nF]     outward unit normal
+    // work list: single-facet-cell facets first (padded to a warp multiple with -1), then facets whose cell owns
+    // >= 2 exterior facets; multi_start is warp aligned
+    const int32_t* work;
+    int64_t n_work, multi_start;
+    // multi-facet cells (SurfaceProjector's 4x4 blocks): per multi facet m = work index - multi_start
+    const int8_t* m_lf;      // [4][nMulti] canonical label a of contributor face (opposite vertex a), -1: none
+    const double* m_w;       // [4*9][nMulti] W[a][j][kk]
+    int64_t nMulti;
+};
+
+struct vh_handle {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+
+    // mesh
+    int64_t nv = 0, nc = 0;
+    double* d_xyz = nullptr;    // [nv][3]
+    int32_t* d_tets = nullptr;  // [nc][4] rows ascending
+    int64_t nF = 0, nBV = 0, nW = 0, nMulti = 0;
+    int32_t *d_facet_cell = nullptr, *d_facet_verts = nullptr, *d_bcell_parent = nullptr, *d_btopology = nullptr,
+            *d_bvert_parent = nullptr;
+    int8_t *d_facet_local = nullptr, *d_bcell_local = nullptr;      // bcell_local AoS [nF][3] (map export)
+    int8_t* d_blocal_soa = nullptr;                                   // [3][nF]
+    double *d_glam = nullptr, *d_normal = nullptr, *d_area = nullptr;  // SoA
+    int32_t* d_work = nullptr;
+    int64_t n_work = 0, multi_start = 0;
+    int8_t* d_m_lf = nullptr;
+    double* d_m_w = nullptr;
+
+    // velocity layout
+    int order = 0, ndof = 0;
+    int64_t n_nodes = 0, vec_len = 0, node_stride = 1;
+    int64_t comp_offset[3] = {0, 0, 0};
+    int32_t* d_facet_nodes = nullptr;  // [ndof][nF] velocity node ids (map export)
+    int32_t* d_slot = nullptr;         // [ndof][nF]
+
+    // run state
+    double mu = 0.0, dt = 0.0;
+    bool begun = false;
+    int64_t count = 0;         // snapshots accumulated
+    bool have_tau_last = false;
+    double* d_sums = nullptr;      // [15][nF]
+    double* d_tau_last[2] = {nullptr, nullptr};  // [9][nF], ping-pong (read by first chunk, written by last)
+    int tau_cur = 0;
+    double* d_part = nullptr;      // [groups][15][nF] partial sums of one launch
+    int64_t part_cap = 0;          // capacity in groups
+    int64_t batch_snapshots = 0, chunk_snapshots = 0;
+
+    // staging (double buffered)
+    double* d_stage[2] = {nullptr, nullptr};
+    int64_t stage_cap = 0;  // snapshots per stage buffer
+    double* d_wss_stage[2] = {nullptr, nullptr};
+    int64_t wss_stage_cap = 0;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_wss[2] = {nullptr, nullptr};
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    void* d_flush = nullptr;
+    int64_t flush_bytes = 0;
+
+    // timers
+    double kernel_ms = 0.0, h2d_ms = 0.0;
+    int64_t launches = 0;
+
+    // NCCL (dlopen'ed)
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
+    double* d_scalar = nullptr;
+};
+
+// ---- K0 (k0_precompute.cu) --------------------------------------------------------------------------------------
+int k0_build_mesh(vh_handle* h, const double* xyz, int64_t nv, const int64_t* tets, int64_t nc);
+int k0_build_velocity_map(vh_handle* h, int order, const double* refined_xyz, int64_t n_nodes, double tol,
+                          const int64_t* node_perm);
+
+// ---- K2/K3/K4 (k2_traction.cu) ------------------------------------------------------------------------------------
+// One launch over `n_snap` resident snapshots (d_u + s * stride_elems).  prev_mode: 0 tau_prev=0, 1 tau_prev from
+// h->d_tau_last, 2 recompute from the snapshot just before d_u (halo).  d_wss (may be null): [n_snap][nF][9].
+int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_elems, int prev_mode, double* d_wss);
+int k4_finalize(vh_handle* h, int64_t n_total, double* d_out5);  // d_out5: 5 arrays [nF*3] TAWSS,OSI,RRT,ECAP,TWSSG
+int k_free_run_buffers(vh_handle* h);
+
+FacetTables vh_tables(const vh_handle* h);
