@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the wall-shear-stress hot path (BASELINE.json metric: wall-facet x snapshots / s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+One *step* is one pass of the whole hot path over the workload's snapshot batch: zero the running sums, per-snapshot
+traction + time reductions for every snapshot (K2/K3), the NCCL all-reduce of the partial sums when N > 1, and the
+final TAWSS/OSI/RRT/ECAP/TWSSG formulas (K4).  ``value`` times that with the snapshots already resident in HBM (CUDA
+events on the launching stream, L2 flushed between steps); ``e2e`` times the same pass through the public Python/C
+ABI call with pinned HOST snapshots (H2D inside) and the D2H read of the five result fields.
+
+Under ``torch.distributed.run`` (N > 1) every rank drives one GPU on its own contiguous time range (weak scaling:
+each rank processes the workload's snapshot count) and rank 0 prints the single JSON line.  No torch is imported.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from vasp_b200 import synth  # noqa: E402
+from vasp_b200.timeshard import env_rank_world  # noqa: E402
+
+METRIC = "wall_facet_snapshots_per_s"
+UNIT = "facet*snapshots/s"
+
+# BASELINE.json configs[1..4]; sizes from SURVEY.md §8 (structured vessel stand-ins, no network for real meshes)
+WORKLOADS = {
+    # offset-stenosis tutorial size: ~14 k fluid tets, P1 velocity, 1000 snapshots
+    "stenosis_p1": dict(n=8, m=36, stenosis=0.45, bulge=0.0, order=1, snapshots=1000,
+                        desc="offset-stenosis tutorial-size cylinder (13.8k tets), P1 velocity, 1000 snapshots"),
+    "aneurysm_p1": dict(n=40, m=208, stenosis=0.0, bulge=0.6, order=1, snapshots=2000,
+                        desc="aneurysm-style fluid mesh (~2M tets), P1 velocity, 2000 snapshots"),
+    "avf_p2": dict(n=52, m=308, stenosis=0.2, bulge=0.0, order=2, snapshots=4000,
+                   desc="AVF-size mesh (~5M tets), P2 velocity, 4000 snapshots"),
+    "vessel10m_p2": dict(n=64, m=407, stenosis=0.0, bulge=0.0, order=2, snapshots=2000,
+                         desc="synthetic 10M-tet vessel, P2 velocity, 2000 snapshots"),
+}
+MU = 3.5e-3
+PERIOD = 0.951  # s, one cardiac cycle of the offset-stenosis problem (simulations/offset_stenosis.py:38-41)
+
+
+def algorithmic_bytes_per_unit(order: int, keep_wss: bool = False) -> int:
+    """8 B x 3 components x (10 | 4) cell dofs, + 72 B if the per-step WSS is written."""
+    return 8 * 3 * (10 if order == 2 else 4) + (72 if keep_wss else 0)
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """NVML samples of SM clock and throttle reasons while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.005):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._period = period_s
+        except Exception as e:  # NVML missing: report that, do not guess
+            self._nv = None
+            self.error = str(e)
+
+    def _loop(self):
+        nv = self._nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                for k, b in names.items():
+                    if bits & b:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(self._period)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if self._nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": getattr(self, "error", "nvml")}
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def build_workload(name: str, n_snap: int, rank: int):
+    w = WORKLOADS[name]
+    mesh = synth.vessel_mesh(w["n"], w["m"], radius=2.0e-3, stenosis=w["stenosis"], bulge=w["bulge"], seed=1234)
+    xyz, tets = mesh["xyz"], mesh["tets"]
+    if w["order"] == 2:
+        points, _, _ = synth.p2_points(xyz, tets, seed=1234)
+    else:
+        points = xyz
+    basis = synth.velocity_basis(points, seed=2024)
+    # weak scaling: rank r owns snapshots [r*n, (r+1)*n) of one long series, plus the halo snapshot before them
+    halo = 1 if rank > 0 else 0
+    dt = PERIOD / n_snap
+    _, coef = synth.velocity_coefficients(n_snap + halo, period=PERIOD, seed=2024, t0=(rank * n_snap - halo) * dt)
+    coef[:, 0] *= 0.3  # m/s scale
+    return dict(xyz=xyz, tets=tets, points=points, basis=basis, coef=coef, dt=dt, halo=halo, order=w["order"],
+                desc=w["desc"])
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    """CPU arm: the restated reference algorithm (oracle/hemo_oracle.c, all host threads) on the same workload."""
+    if rank != 0:
+        return
+    from oracle import c_oracle, hemo_oracle as ho
+    wl = build_workload(args.workload, args.snapshots, 0)
+    stress = ho.SurfaceStress(wl["xyz"], wl["tets"], MU, wl["order"],
+                              None if wl["order"] == 1 else ho.match_points(
+                                  ho.p2_node_coordinates(wl["xyz"], ho.p2_cell_nodes(wl["tets"])[1]), wl["points"],
+                                  1e-8 * float(np.ptp(wl["points"], axis=0).max())))
+    co = c_oracle.COracle(stress)
+    n = len(wl["points"])
+    threads = c_oracle.max_threads()
+    # bounded sample: at most ~2 s of work per step
+    n_s = min(args.snapshots, max(threads, int(2.0e6 * threads / max(stress.nF, 1))))
+    u = synth.velocity_series(wl["basis"], wl["coef"][:n_s])
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        res = co.run(u, wl["dt"], (0, n, 2 * n), threads=threads)
+        ho.finalize(res["wss_sum"], res["tawss_sum"], res["twssg_sum"], res["count"])
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    t = float(np.mean(times))
+    value = stress.nF * n_s / t
+    sample = f"{n_s} of {args.snapshots} snapshots x {stress.nF} facets per step"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}", "facets": stress.nF,
+                       "snapshots_per_gpu": args.snapshots, "order": wl["order"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference = FEniCS path restated in C (oracle/hemo_oracle.c); dolfin itself is not installable"}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank: int, local_rank: int, world: int) -> None:
+    from vasp_b200.engine import HemoEngine, pinned_empty
+    from vasp_b200.timeshard import NcclComm
+
+    wl = build_workload(args.workload, args.snapshots, rank)
+    n_snap, halo, order = args.snapshots, wl["halo"], wl["order"]
+    eng = HemoEngine(local_rank)
+    eng.set_mesh(wl["xyz"], wl["tets"])
+    if order == 2:
+        eng.set_velocity_layout(2, refined_xyz=wl["points"])
+    else:
+        eng.set_velocity_layout(1)
+    nF, vec_len = eng.nF, eng.vec_len
+    comm = NcclComm(eng, rank, world) if world > 1 else None
+
+    # inputs: pinned host copy (e2e) and a resident device copy (value)
+    u_host = pinned_empty((n_snap + halo, vec_len))
+    synth.velocity_series(wl["basis"], wl["coef"], out=u_host)
+    d_u = eng.device_alloc(u_host.nbytes)
+    eng.h2d(d_u, u_host)
+    flags = 2 if halo else 1
+    stride = vec_len * 8
+    n_total = n_snap * world
+
+    def step_resident():
+        eng.begin(MU, wl["dt"])
+        eng.push_device(d_u, n_snap + halo, stride, flags)
+        if comm:
+            comm.allreduce_sums()
+        eng.finalize_async(n_total)
+
+    def step_e2e():
+        eng.begin(MU, wl["dt"])
+        eng.push(u_host, flags=flags)
+        if comm:
+            comm.allreduce_sums()
+        return eng.finalize(n_total)
+
+    for _ in range(args.warmup):
+        eng.flush_l2()
+        step_resident()
+    eng.sync()
+    if comm:
+        comm.barrier()
+    eng.set_profile(True)
+    launches0 = eng.timers()["launches"]
+    step_ms = []
+    with ClockSampler(local_rank) as clk:
+        for _ in range(args.steps):
+            eng.flush_l2()          # inputs (72 MB here) are smaller than the 126 MB L2: evict between steps
+            eng.sync()
+            eng.timer_start()
+            step_resident()
+            step_ms.append(eng.timer_stop())
+        eng.sync()
+    if comm:
+        comm.barrier()
+    k2_ms, k2_n = eng.kernel_profile()
+    eng.set_profile(False)
+    launches = eng.timers()["launches"] - launches0  # k2 + k3 + k4 per step (the untimed L2 flush is not counted)
+    total_ms = float(np.sum(step_ms))
+    if comm:
+        total_ms = comm.max(total_ms)
+    ms_per_step = total_ms / args.steps
+    value = world * nF * n_snap / (ms_per_step * 1e-3)
+
+    # end to end through the public API: pinned host snapshots in, five result fields out
+    e2e_steps = max(1, min(args.steps, 10))
+    step_e2e()
+    eng.sync()
+    if comm:
+        comm.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = step_e2e()
+    eng.sync()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if comm:
+        e2e_s = comm.max(e2e_s)
+    e2e_value = world * nF * n_snap / e2e_s
+    h2d_bytes = int((n_snap + halo) * vec_len * 8)
+    d2h_bytes = int(5 * 3 * nF * 8)
+    osi = out["OSI"]
+    sane = bool(np.isfinite(out["TAWSS"]).all() and np.nanmin(osi) >= -1e-12 and np.nanmax(osi) <= 0.5 + 1e-12)
+
+    if rank != 0:
+        eng.device_free(d_u)
+        return
+    peak, peak_src = measured_peak_gbs()
+    b_alg = algorithmic_bytes_per_unit(order)
+    units_per_launch = nF * n_snap
+    k2_avg_ms = k2_ms / max(k2_n, 1)
+    achieved = units_per_launch * b_alg / (k2_avg_ms * 1e-3) / 1e9
+    traffic = None
+    tfile = ROOT / "profiles" / "k2_traffic.json"  # written from an `ncu --set full` capture of this command
+    if tfile.exists():
+        try:
+            traffic = json.loads(tfile.read_text()).get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(wl, n_snap)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "facets": nF, "snapshots_per_gpu": n_snap,
+                   "order": order, "velocity_nodes": int(len(wl["points"])), "tets": int(len(wl["tets"])),
+                   "parallelism": f"time-shard x{world}", "l2": "flushed between timed steps (512 MiB write)",
+                   "results_sane": sane},
+        "clocks": clk.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": f"k2_traction<{order}>", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_unit": b_alg, "units_per_launch": units_per_launch,
+                     "kernel_ms_per_launch": k2_avg_ms, "launches_timed": k2_n},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    eng.device_free(d_u)
+
+
+def cpu_baseline(wl, n_snap: int):
+    """Oracle C port on the host cores (bounded sample of the same workload), rank 0 at N = 1 only."""
+    from oracle import c_oracle, hemo_oracle as ho
+    node_of_p2 = None
+    if wl["order"] == 2:
+        p2 = ho.p2_node_coordinates(wl["xyz"], ho.p2_cell_nodes(wl["tets"])[1])
+        node_of_p2 = ho.match_points(p2, wl["points"], 1e-8 * float(np.ptp(wl["points"], axis=0).max()))
+    stress = ho.SurfaceStress(wl["xyz"], wl["tets"], MU, wl["order"], node_of_p2)
+    co = c_oracle.COracle(stress)
+    threads = c_oracle.max_threads()
+    n = len(wl["points"])
+    n_s = min(n_snap, max(threads, int(4.0e6 * threads / max(stress.nF, 1))))
+    u = synth.velocity_series(wl["basis"], wl["coef"][wl["halo"]:wl["halo"] + n_s])
+    co.run(u[:max(1, n_s // 8)], wl["dt"], (0, n, 2 * n), threads=threads)  # warm-up
+    reps, t_best = 0, float("inf")
+    t_start = time.perf_counter()
+    while reps < 5 and time.perf_counter() - t_start < 20.0:
+        t0 = time.perf_counter()
+        co.run(u, wl["dt"], (0, n, 2 * n), threads=threads)
+        t_best = min(t_best, time.perf_counter() - t0)
+        reps += 1
+    return {"value": stress.nF * n_s / t_best, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n_s} of {n_snap} snapshots x {stress.nF} facets, best of {reps}",
+            "note": "optimistic stand-in: the FEniCS original adds Python dof matching + global LU per snapshot"}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="stenosis_p1")
+    ap.add_argument("--snapshots", type=int, default=None, help="snapshots per GPU (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rules: at least three warm-up steps
+    if args.snapshots is None:
+        args.snapshots = WORKLOADS[args.workload]["snapshots"]
+    rank, local_rank, world = env_rank_world()
+    if world == 1 and args.gpus > 1:
+        # launched plainly with --gpus N: re-exec under the launcher the driver would use
+        import socket
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                   f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+                                   "--master-port", str(port), str(Path(__file__).resolve()), *sys.argv[1:]])
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -100,7 +100,8 @@ int vh_push_snapshots_device(vh_handle* h, const double* d_u, int64_t n_snap, in
                              double* d_wss_out);
 
 /* ---- reductions / results ------------------------------------------------------------------------------- */
-/* Running sums as 15*nF doubles: [wss_sum nF*9 | tawss_sum nF*3 | twssg_sum nF*3], count = snapshots added. */
+/* Running sums as 15 rows of nF doubles (SoA): rows 0-8 sum tau (row 3*j+c: boundary dof j, component c),
+ * rows 9-11 sum |tau| (dof j), rows 12-14 sum P(|dtau/dt|) (dof j); count = snapshots added. */
 int vh_get_sums(vh_handle* h, double* sums, int64_t* count);
 int vh_set_sums(vh_handle* h, const double* sums, int64_t count);
 /* Device pointer to the same 15*nF block (for NCCL or peer access). */
@@ -108,14 +109,19 @@ int vh_sums_device_ptr(vh_handle* h, double** d_sums);
 /* tau of the last snapshot pushed ([facet][j][c]); needed by nobody but tests and hand-offs between shards. */
 int vh_get_tau_last(vh_handle* h, double* tau);
 
-/* Final formulas (:326-346) on the device, each output nF*3 doubles (any may be NULL). */
+/* Final formulas (:326-346) on the device, each output nF*3 doubles (any may be NULL; with all NULL the call only
+ * enqueues the kernel and the results stay in device memory). */
 int vh_finalize(vh_handle* h, int64_t n_total, double* tawss, double* osi, double* rrt, double* ecap,
                 double* twssg);
 
 int vh_sync(vh_handle* h);
 /* Milliseconds spent in kernels / in H2D copies since vh_begin (CUDA events), and number of kernel launches. */
 int vh_get_timers(vh_handle* h, double* kernel_ms, double* h2d_ms, int64_t* launches);
-/* Event-timed execution of fn-less region: start/stop markers on the compute stream. */
+/* Per-launch CUDA-event timing of the dominant kernel (k2_traction), for the roofline: switch on, run, then read
+ * the summed duration and launch count since the last read (reading synchronises and resets). */
+int vh_set_profile(vh_handle* h, int on);
+int vh_get_kernel_profile(vh_handle* h, double* k2_ms, int64_t* k2_launches);
+/* Start/stop markers on the compute stream (CUDA events); stop synchronises and returns the elapsed ms. */
 int vh_timer_start(vh_handle* h);
 int vh_timer_stop(vh_handle* h, double* ms);
 

@@ -64,6 +64,7 @@ int ensure_run_buffers(vh_handle* h) {
         VH_CUDA(cudaMalloc(&h->d_sums, sizeof(double) * VH_NSUM * nF));
         VH_CUDA(cudaMalloc(&h->d_tau_last[0], sizeof(double) * 9 * nF));
         VH_CUDA(cudaMalloc(&h->d_tau_last[1], sizeof(double) * 9 * nF));
+        VH_CUDA(cudaMalloc(&h->d_out5, sizeof(double) * 15 * nF));
     }
     return VH_OK;
 }
@@ -141,6 +142,7 @@ int vh_destroy(vh_handle* h) {
     cudaEventDestroy(h->ev_t1);
     cudaEventDestroy(h->ev_k0);
     cudaEventDestroy(h->ev_k1);
+    for (auto& e : h->prof_pool) cudaEventDestroy(e);
     cudaStreamDestroy(h->s_compute);
     cudaStreamDestroy(h->s_copy);
     delete h;
@@ -233,8 +235,7 @@ int vh_begin(vh_handle* h, double mu, double dt) {
     VH_CUDA(cudaMemsetAsync(h->d_sums, 0, sizeof(double) * VH_NSUM * h->nF, h->s_compute));
     VH_CUDA(cudaMemsetAsync(h->d_tau_last[0], 0, sizeof(double) * 9 * h->nF, h->s_compute));
     VH_CUDA(cudaMemsetAsync(h->d_tau_last[1], 0, sizeof(double) * 9 * h->nF, h->s_compute));
-    VH_CUDA(cudaStreamSynchronize(h->s_compute));
-    h->begun = true;
+    h->begun = true;  // stream-ordered: no host sync needed before the first push
     return VH_OK;
 }
 
@@ -432,25 +433,17 @@ int vh_finalize(vh_handle* h, int64_t n_total, double* tawss, double* osi, doubl
     VH_TRY(check_ready(h, "vh_finalize"));
     VH_CHECK(n_total > 0, VH_ERR_ARG, "vh_finalize: n_total must be positive");
     const int64_t n3 = 3 * h->nF;
-    double* d_out = nullptr;
-    VH_CUDA(cudaMalloc(&d_out, sizeof(double) * 5 * n3));
-    int rc = k4_finalize(h, n_total, d_out);
+    VH_TRY(k4_finalize(h, n_total, h->d_out5));
     double* outs[5] = {tawss, osi, rrt, ecap, twssg};
-    for (int i = 0; i < 5 && rc == VH_OK; ++i) {
+    bool any = false;
+    for (int i = 0; i < 5; ++i) {
         if (!outs[i]) continue;
-        cudaError_t e = cudaMemcpyAsync(outs[i], d_out + i * n3, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->s_compute);
-        if (e != cudaSuccess) {
-            vh_set_error("vh_finalize: D2H failed: %s", cudaGetErrorString(e));
-            rc = VH_ERR_CUDA;
-        }
+        any = true;
+        VH_CUDA(cudaMemcpyAsync(outs[i], h->d_out5 + i * n3, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->s_compute));
     }
-    cudaError_t e = cudaStreamSynchronize(h->s_compute);
-    cudaFree(d_out);
-    if (rc == VH_OK && e != cudaSuccess) {
-        vh_set_error("vh_finalize: %s", cudaGetErrorString(e));
-        rc = VH_ERR_CUDA;
-    }
-    return rc;
+    // with no host outputs the call stays asynchronous (device-resident timing); results remain in HBM
+    if (any) VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    return VH_OK;
 }
 
 int vh_sync(vh_handle* h) {
@@ -466,6 +459,34 @@ int vh_get_timers(vh_handle* h, double* kernel_ms, double* h2d_ms, int64_t* laun
     if (kernel_ms) *kernel_ms = h->kernel_ms;
     if (h2d_ms) *h2d_ms = h->h2d_ms;
     if (launches) *launches = h->launches;
+    return VH_OK;
+}
+
+int vh_set_profile(vh_handle* h, int on) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_set_profile: null handle");
+    VH_CUDA(cudaSetDevice(h->device));
+    if (on && h->prof_pool.empty()) {
+        h->prof_pool.resize(1024);
+        for (auto& e : h->prof_pool) VH_CUDA(cudaEventCreate(&e));
+    }
+    h->profile = on != 0;
+    h->prof_used = 0;
+    return VH_OK;
+}
+
+int vh_get_kernel_profile(vh_handle* h, double* k2_ms, int64_t* k2_launches) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_get_kernel_profile: null handle");
+    VH_CUDA(cudaSetDevice(h->device));
+    VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+        float ms = 0.f;
+        VH_CUDA(cudaEventElapsedTime(&ms, h->prof_pool[i], h->prof_pool[i + 1]));
+        tot += ms;
+    }
+    if (k2_ms) *k2_ms = tot;
+    if (k2_launches) *k2_launches = (int64_t)(h->prof_used / 2);
+    h->prof_used = 0;
     return VH_OK;
 }
 

@@ -89,6 +89,7 @@ struct vh_handle {
     double* d_sums = nullptr;      // [15][nF]
     double* d_tau_last[2] = {nullptr, nullptr};  // [9][nF], ping-pong (read by first chunk, written by last)
     int tau_cur = 0;
+    double* d_out5 = nullptr;      // [5][3*nF] TAWSS, OSI, RRT, ECAP, TWSSG
     double* d_part = nullptr;      // [groups][15][nF] partial sums of one launch
     int64_t part_cap = 0;          // capacity in groups
     int64_t batch_snapshots = 0, chunk_snapshots = 0;
@@ -106,6 +107,10 @@ struct vh_handle {
     // timers
     double kernel_ms = 0.0, h2d_ms = 0.0;
     int64_t launches = 0;
+    // per-launch timing of the dominant kernel (k2_traction) for the roofline: event pairs from a pre-made pool
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_pool;
+    size_t prof_used = 0;
 
     // NCCL (dlopen'ed)
     void* nccl_comm = nullptr;

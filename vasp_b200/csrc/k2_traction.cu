@@ -367,7 +367,8 @@ int k_free_run_buffers(vh_handle* h) {
     if (h->d_tau_last[0]) cudaFree(h->d_tau_last[0]);
     if (h->d_tau_last[1]) cudaFree(h->d_tau_last[1]);
     if (h->d_part) cudaFree(h->d_part);
-    h->d_sums = h->d_tau_last[0] = h->d_tau_last[1] = h->d_part = nullptr;
+    if (h->d_out5) cudaFree(h->d_out5);
+    h->d_sums = h->d_tau_last[0] = h->d_tau_last[1] = h->d_part = h->d_out5 = nullptr;
     h->part_cap = 0;
     for (int i = 0; i < 2; ++i) {
         if (h->d_stage[i]) cudaFree(h->d_stage[i]);
@@ -424,10 +425,16 @@ int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_el
     a.off2 = h->comp_offset[2];
     dim3 grid((unsigned)gx, (unsigned)gy), block(bx, by);
     size_t smem = by > 1 ? sizeof(double) * VH_NSUM * bx * by : 0;
+    const bool prof = h->profile && h->prof_used + 2 <= h->prof_pool.size();
+    if (prof) cudaEventRecord(h->prof_pool[h->prof_used], h->s_compute);
     if (h->order == 2)
         k2_traction<2><<<grid, block, smem, h->s_compute>>>(a);
     else
         k2_traction<1><<<grid, block, smem, h->s_compute>>>(a);
+    if (prof) {
+        cudaEventRecord(h->prof_pool[h->prof_used + 1], h->s_compute);
+        h->prof_used += 2;
+    }
     VH_CUDA(cudaGetLastError());
     const int64_t n = VH_NSUM * nF;
     k3_fold<<<(unsigned)((n + 255) / 256), 256, 0, h->s_compute>>>(h->d_sums, h->d_part, n, gy);

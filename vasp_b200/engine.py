@@ -196,6 +196,19 @@ class HemoEngine:
         check(self._lib.vh_get_timers(self._h, C.byref(k), C.byref(c), C.byref(n)))
         return {"kernel_ms": k.value, "h2d_ms": c.value, "launches": int(n.value)}
 
+    def set_profile(self, on: bool) -> None:
+        check(self._lib.vh_set_profile(self._h, int(bool(on))))
+
+    def kernel_profile(self) -> Tuple[float, int]:
+        """(summed k2_traction milliseconds, launches) since the last call."""
+        ms, n = C.c_double(), C.c_int64()
+        check(self._lib.vh_get_kernel_profile(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, int(n.value)
+
+    def finalize_async(self, n_total: int) -> None:
+        """Enqueue the final formulas only; results stay on the device (bench: device-resident timing)."""
+        check(self._lib.vh_finalize(self._h, int(n_total), None, None, None, None, None))
+
     def timer_start(self) -> None:
         check(self._lib.vh_timer_start(self._h))
 

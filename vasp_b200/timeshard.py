@@ -1,0 +1,199 @@
+"""Multi-GPU time sharding: contiguous snapshot ranges per rank, one halo snapshot, one all-reduce.
+
+The reference's snapshot loop is strictly sequential (``compute_hemodynamics.py:272-318``); the only coupling
+between snapshots is additive (``TAWSS``, ``WSS_mean``, ``TWSSG`` sums, ``:303-312``) plus TWSSG's dependence on
+the previous step's tau (``:309,315-316``).  So rank ``g`` takes snapshots ``[k_g, k_{g+1})``, additionally reads
+snapshot ``k_g - 1`` to seed ``tau_prev`` (rank 0 starts from zero as the reference does, ``:244``), and the
+``15 * nF`` partial sums are added across ranks once before the final formulas (``:326-346``).  SURVEY.md §8e.
+
+One process per GPU.  The launcher contract is torchrun's environment (``RANK``, ``LOCAL_RANK``, ``WORLD_SIZE``,
+``MASTER_PORT``) but torch itself is not needed: the NCCL unique id travels through a file on the node.
+"""
+from __future__ import annotations
+
+import os
+import time
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Callable, Optional, Protocol, Tuple
+
+import numpy as np
+
+from ._lib import PUSH_GLOBAL_FIRST, PUSH_HALO_FIRST
+
+
+def env_rank_world() -> Tuple[int, int, int]:
+    """(rank, local_rank, world_size) from the launcher's environment; (0, 0, 1) when run plainly."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    return rank, local, world
+
+
+@dataclass(frozen=True)
+class Shard:
+    """Snapshots ``[start, stop)`` of the selected series belong to this rank; ``read_start`` is where reading
+    begins (one earlier than ``start`` when a halo snapshot is needed)."""
+    rank: int
+    world: int
+    start: int
+    stop: int
+
+    @property
+    def has_halo(self) -> bool:
+        return self.start > 0 and self.stop > self.start
+
+    @property
+    def read_start(self) -> int:
+        return self.start - 1 if self.has_halo else self.start
+
+    @property
+    def count(self) -> int:
+        return self.stop - self.start
+
+    def first_push_flags(self) -> int:
+        return PUSH_HALO_FIRST if self.has_halo else PUSH_GLOBAL_FIRST
+
+
+def plan_shard(n_snap: int, rank: int, world: int) -> Shard:
+    """Contiguous, balanced ranges: the first ``n_snap % world`` ranks get one extra snapshot."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    base, extra = divmod(n_snap, world)
+    start = rank * base + min(rank, extra)
+    stop = start + base + (1 if rank < extra else 0)
+    return Shard(rank, world, start, stop)
+
+
+class Engine(Protocol):
+    """What :func:`run_shard` needs from a compute engine (``HemoEngine`` satisfies it)."""
+
+    def push(self, u: np.ndarray, flags: int = 0, keep_wss: bool = False, wss_out=None): ...
+
+
+def run_shard(engine: Engine, shard: Shard, read_block: Callable[[int, int], np.ndarray], block: int,
+              on_wss: Optional[Callable[[int, np.ndarray], None]] = None) -> int:
+    """Stream this rank's snapshots through ``engine`` in blocks of ``block`` snapshots.
+
+    ``read_block(a, b)`` returns snapshots ``[a, b)`` as a ``(b - a, vec_len)`` float64 array.  ``on_wss(k, tau)``
+    receives the per-step WSS of global snapshots ``k, k+1, ...`` when given.  Returns the snapshots processed.
+    """
+    pos = shard.read_start
+    first = True
+    done = 0
+    while pos < shard.stop:
+        end = min(pos + block, shard.stop)
+        if first and shard.has_halo and end - pos < 2:
+            end = min(pos + 2, shard.stop)  # the halo must travel with at least one real snapshot
+        u = read_block(pos, end)
+        flags = shard.first_push_flags() if first else 0
+        wss = engine.push(u, flags=flags, keep_wss=on_wss is not None)
+        n_real = (end - pos) - (1 if (first and shard.has_halo) else 0)
+        if on_wss is not None and n_real:
+            on_wss(shard.start + done, wss)
+        done += n_real
+        pos = end
+        first = False
+    return done
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# communicators
+# ------------------------------------------------------------------------------------------------------------------
+def exchange_unique_id(rank: int, world: int, make_id: Callable[[], bytes], timeout: float = 300.0,
+                       directory: Optional[str] = None) -> bytes:
+    """Rank 0 creates the NCCL unique id and publishes it through a file; the other ranks of the node poll for it.
+
+    The file name carries the launcher's pid (all workers of one torchrun share their parent) and MASTER_PORT, so
+    concurrent or consecutive jobs cannot pick up each other's id; rank 0 removes any stale file first and every
+    rank checks a nonce made of the launcher pid and start time."""
+    tag = f"{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}_{os.environ.get('TORCHELASTIC_RUN_ID', 'none')}"
+    d = Path(directory or os.environ.get("VASP_B200_RDZV_DIR", "/tmp"))
+    path = d / f"vasp_b200_nccl_{tag}_{world}.id"
+    if rank == 0:
+        uid = make_id()
+        tmp = path.with_suffix(f".tmp{os.getpid()}")
+        tmp.write_bytes(uid)
+        os.replace(tmp, path)
+        return uid
+    t0 = time.time()
+    my_start = _process_start_time()
+    while time.time() - t0 < timeout:
+        try:
+            st = path.stat()
+            # a file older than this job's processes is a leftover of a crashed run with a recycled pid
+            if st.st_size == 128 and st.st_mtime >= my_start - 120.0:
+                return path.read_bytes()
+        except FileNotFoundError:
+            pass
+        time.sleep(0.02)
+    raise TimeoutError(f"rank {rank}: NCCL unique id file {path} did not appear within {timeout}s")
+
+
+def _process_start_time() -> float:
+    try:
+        return os.stat(f"/proc/{os.getpid()}").st_ctime
+    except OSError:
+        return time.time()
+
+
+def cleanup_unique_id(world: int, directory: Optional[str] = None) -> None:
+    tag = f"{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}_{os.environ.get('TORCHELASTIC_RUN_ID', 'none')}"
+    d = Path(directory or os.environ.get("VASP_B200_RDZV_DIR", "/tmp"))
+    try:
+        (d / f"vasp_b200_nccl_{tag}_{world}.id").unlink()
+    except FileNotFoundError:
+        pass
+
+
+class NcclComm:
+    """Device-side reduction through the engine's own NCCL communicator (the product path)."""
+
+    def __init__(self, engine, rank: int, world: int):
+        from .engine import HemoEngine
+        self.engine, self.rank, self.world = engine, rank, world
+        uid = exchange_unique_id(rank, world, HemoEngine.nccl_unique_id)
+        engine.nccl_init(uid, rank, world)
+        engine.barrier()
+        if rank == 0:
+            cleanup_unique_id(world)
+
+    def allreduce_sums(self) -> None:
+        self.engine.allreduce_sums()
+
+    def max(self, value: float) -> float:
+        return self.engine.allreduce_max(value)
+
+    def barrier(self) -> None:
+        self.engine.barrier()
+
+
+class TorchDistComm:
+    """Same contract over an initialised ``torch.distributed`` process group (any backend).
+
+    The partial sums make one host round trip; used when the caller already owns a process group (and by the
+    world_size-2 ``gloo`` tests, where the engine is a CPU stand-in)."""
+
+    def __init__(self, engine):
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed process group is not initialised")
+        self.engine, self._dist = engine, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def allreduce_sums(self) -> None:
+        import torch
+        sums, count = self.engine.sums()
+        t = torch.from_numpy(np.concatenate([sums.ravel(), [float(count)]]))
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM)
+        out = t.numpy()
+        self.engine.set_sums(out[:-1].reshape(sums.shape), int(round(out[-1])))
+
+    def max(self, value: float) -> float:
+        import torch
+        t = torch.tensor([float(value)], dtype=torch.float64)
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def barrier(self) -> None:
+        self._dist.barrier()
