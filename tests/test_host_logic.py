@@ -1,0 +1,174 @@
+"""Host-side logic that needs no GPU: dataset selection, dof-layout detection, outputs, CLI contract, shard plans,
+and that the C-ABI library loads and exports every symbol the header declares."""
+import ctypes
+import json
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+from vasp_b200 import _lib, io_dolfin, synth, timeshard
+from vasp_b200.h5lite import H5File, H5Writer
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    header = (ROOT / "include" / "vasp_hemo.h").read_text()
+    declared = set(re.findall(r"\b(vh_[a-z0-9_]+)\s*\(", header)) - {"vh_handle", "vh_status"}
+    assert len(declared) >= 35
+    assert _lib.LIB_PATH.exists(), "libvasp_hemo.so not built: run __graft_entry__.build()"
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))   # loading needs no GPU; compute calls would fail loudly
+    missing = sorted(s for s in declared if not hasattr(lib, s))
+    assert not missing, missing
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+
+
+def test_no_gpu_means_loud_failure_not_a_fallback():
+    lib = _lib.load()
+    n = ctypes.c_int(0)
+    rc = lib.vh_device_count(ctypes.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a GPU is visible here")
+    h = ctypes.c_void_p()
+    assert lib.vh_create(0, ctypes.byref(h)) != 0
+    from vasp_b200.engine import HemoEngine
+    with pytest.raises(_lib.VaspHemoError):
+        HemoEngine(0)
+
+
+def test_product_never_imports_the_oracle():
+    for p in (ROOT / "vasp_b200").rglob("*.py"):
+        src = p.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), p
+        assert "torch" not in re.findall(r"^\s*(?:from|import)\s+(\w+)", src, re.M) or p.name == "timeshard.py", p
+
+
+def test_get_dataset_names_selection_rule(tmp_path):
+    p = tmp_path / "u.h5"
+    with H5Writer(p) as w:
+        for k in (2, 3, 4, 5, 6, 8, 9):
+            w.create_dataset(f"/velocity/vector_{k}", np.zeros(3), attrs={"timestamp": float(k)})
+        w.create_dataset("/velocity/cells", np.zeros(1))
+    with H5File(p) as f:
+        g = f["velocity"]
+        assert io_dolfin.get_dataset_names(g, step=1) == [f"vector_{k}" for k in (2, 3, 4, 5, 6, 8, 9)]
+        assert io_dolfin.get_dataset_names(g, step=2) == [f"vector_{k}" for k in (2, 4, 6, 8)]
+        assert io_dolfin.get_dataset_names(g, step=3) == [f"vector_{k}" for k in (3, 6, 9)]
+
+
+@pytest.mark.parametrize("kind", ["blocked", "interleaved", "blocked_perm", "no_tables"])
+def test_velocity_layout_detection(tmp_path, kind):
+    src = H.load_fluid("cylinder")
+    rx, rt = synth.refine_uniform(src["xyz"], src["tets"], seed=3)
+    n, nc = len(rx), len(rt)
+    rng = np.random.default_rng(0)
+    q = rng.permutation(n)
+    vals = rng.random((3, n))                       # value of (comp, refined vertex)
+    if kind in ("blocked", "no_tables"):
+        idx = np.arange(3)[:, None] * n + np.arange(n)[None, :]
+    elif kind == "interleaved":
+        idx = 3 * q[None, :] + np.arange(3)[:, None]
+    else:
+        idx = np.arange(3)[:, None] * n + q[None, :]
+    vec = np.empty(3 * n)
+    vec[idx] = vals
+    p = tmp_path / "u.h5"
+    with H5Writer(p) as w:
+        for k in range(2):
+            w.create_dataset(f"/velocity/vector_{k}", vec, attrs={"timestamp": 0.1 * k})
+        if kind != "no_tables":
+            cell_dofs = idx[:, rt].transpose(1, 0, 2).reshape(-1)   # per cell: comp-major, 4 vertices
+            w.create_dataset("/velocity/cell_dofs", cell_dofs.astype("<i8"))
+            w.create_dataset("/velocity/x_cell_dofs", (12 * np.arange(nc + 1)).astype("<i8"))
+            w.create_dataset("/velocity/cells", np.arange(nc, dtype="<i8"))
+    s = io_dolfin.VelocitySeries(p)
+    off, stride, perm = s.layout(rt, n)
+    pv = np.arange(n) if perm is None else perm
+    for c in range(3):
+        assert np.array_equal(vec[off[c] + stride * pv], vals[c])
+    assert s.timestamps.tolist() == [0.0, 0.1] and s.vec_len == 3 * n
+    buf = np.zeros((2, 3 * n + 5))
+    s.read_into(buf, 0, 2)
+    assert np.array_equal(buf[1, :3 * n], vec)
+    s.close()
+
+
+def test_checkpoint_writer_layout(tmp_path):
+    """Member names and shapes the reference's own consumer dereferences
+    (postprocessing_h5py_common.py:234-242,271,337-343) and regexes it parses XDMF with
+    (postprocessing_common.py:92-94)."""
+    nF, nBV = 5, 7
+    rng = np.random.default_rng(1)
+    topo, geom = rng.integers(0, nBV, (nF, 3)), rng.random((nBV, 3))
+    w = io_dolfin.CheckpointWriter(tmp_path, "WSS", topo, geom, True)
+    vals = [rng.random((nF, 3, 3)) for _ in range(3)]
+    for k, v in enumerate(vals):
+        w.write(v, 0.5 + 0.1 * k)
+    w.close()
+    with H5File(tmp_path / "WSS.h5") as f:
+        assert list(f.keys()) == ["WSS"]
+        assert sorted(f["WSS"].keys()) == ["WSS_0", "WSS_1", "WSS_2"]
+        for member in ("cell_dofs", "cells", "mesh/geometry", "mesh/topology", "x_cell_dofs"):
+            assert member in f["WSS/WSS_0"]
+        assert f["WSS/WSS_2/vector"].shape == (9 * nF, 1)
+        assert np.array_equal(f["WSS/WSS_1/vector"].read().reshape(nF, 3, 3), vals[1])   # node-interleaved xyz
+        assert f["WSS/WSS_0/mesh/topology"].shape == (nF, 3) and f["WSS/WSS_0/mesh/geometry"].shape == (nBV, 3)
+    for k in range(3):
+        r = io_dolfin.read_checkpoint(tmp_path, "WSS", k)["values"]            # per cell: comp-major (UFC)
+        assert np.array_equal(r.reshape(nF, 3, 3).transpose(0, 2, 1), vals[k])
+    x = (tmp_path / "WSS.xdmf").read_text()
+    assert re.findall('<Time Value="(.+?)"', x) == ["0.5", "0.6", "0.7"]
+    assert re.findall(r'"HDF">(.*?):', x)[0] == "WSS.h5"
+    assert [int(i) for i in re.findall(r'_([0-9]+)\/vector', x)] == [0, 1, 2]
+    assert 'ElementFamily="DG" ElementDegree="1" ElementCell="triangle"' in x and 'AttributeType="Vector"' in x
+    s = io_dolfin.CheckpointWriter(tmp_path, "TAWSS", topo, geom, False)
+    s.write(rng.random((nF, 3)), 0)
+    s.close()
+    assert 'AttributeType="Scalar"' in (tmp_path / "TAWSS.xdmf").read_text()
+    with H5File(tmp_path / "TAWSS.h5") as f:
+        assert f["TAWSS/TAWSS_0/vector"].shape == (3 * nF, 1)
+
+
+def test_shard_plan_covers_the_series_once():
+    for n, world in ((10, 1), (10, 3), (7, 8), (2000, 8), (5, 5)):
+        shards = [timeshard.plan_shard(n, r, world) for r in range(world)]
+        assert shards[0].start == 0 and shards[-1].stop == n
+        assert all(a.stop == b.start for a, b in zip(shards, shards[1:]))
+        assert max(s.count for s in shards) - min(s.count for s in shards) <= 1
+        assert not shards[0].has_halo and shards[0].first_push_flags() == 1
+        for s in shards[1:]:
+            assert s.has_halo == (s.count > 0)
+            if s.has_halo:
+                assert s.read_start == s.start - 1 and s.first_push_flags() == 2
+
+
+def test_cli_flag_set_and_error_conventions(tmp_path, monkeypatch):
+    from vasp_b200 import compute_hemodynamics as ch
+    a = ch.parse_arguments(["--folder", "x", "--mesh-path", "m.h5", "--stride", "3", "-st", "0.1", "-et", "0.9",
+                            "--extract-entire-domain", "--log-level", "10"])
+    assert (a.folder, a.mesh_path, a.stride, a.start_time, a.end_time, a.extract_entire_domain, a.log_level) == \
+        (Path("x"), Path("m.h5"), 3, 0.1, 0.9, True, 10)
+    d = ch.parse_arguments(["--folder", "x"])
+    assert (d.mesh_path, d.stride, d.start_time, d.end_time, d.extract_entire_domain, d.log_level) == \
+        (None, 1, None, None, False, 20)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    with pytest.raises(AssertionError, match="not found"):
+        ch.main(["--folder", str(tmp_path / "missing")])
+    with pytest.raises(RuntimeError, match="Error reading parameters from file."):
+        ch.main(["--folder", str(tmp_path)])                       # no Checkpoint/default_variables.json
+    (tmp_path / "Checkpoint").mkdir()
+    (tmp_path / "Checkpoint" / "default_variables.json").write_text("{not json")
+    with pytest.raises(RuntimeError):
+        ch.main(["--folder", str(tmp_path)])
+    (tmp_path / "Checkpoint" / "default_variables.json").write_text(json.dumps({"save_deg": 1, "mu_f": [1.0, 2.0]}))
+    (tmp_path / "Visualization_separate_domain").mkdir()
+    with pytest.raises(AssertionError, match="save_deg = 2"):
+        ch.main(["--folder", str(tmp_path)])
+    (tmp_path / "Checkpoint" / "default_variables.json").write_text(json.dumps({"save_deg": 2, "mu_f": 1.0}))
+    with pytest.raises(AssertionError, match="Mesh file"):
+        ch.main(["--folder", str(tmp_path)])
+    assert ch.compute_hemodynamics is ch.compute_hemodyanamics
+    assert ch.read_parameters_from_file(tmp_path) == {"save_deg": 2, "mu_f": 1.0}

@@ -1,0 +1,156 @@
+"""Pins for the CPU oracle: the reference's own known-answer test, dolfin's facet order, closed forms, the C twin."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, hemo_oracle as ho
+from tests import helpers as H
+from vasp_b200 import synth
+
+GOLDEN = Path(__file__).parent / "golden"
+
+
+def _pipe_p2():
+    src = H.load_pipe()
+    cn, edges = ho.p2_cell_nodes(src["tets"])
+    pts = ho.p2_node_coordinates(src["xyz"], edges)
+    return src, pts
+
+
+def test_poiseuille_known_answer_of_the_reference_test():
+    """tests/test_compute_hemodynamics.py:9-88 of the reference: G=4, mu=1, R=1 => WSS = 2; wall-averaged TAWSS
+    over boundary cells with 0.1 < x < 4.9 must be in (1.95, 2.05); OSI in [-1e-12, 0.5+1e-12]."""
+    src, pts = _pipe_p2()
+    n = len(pts)
+    assert src["params"]["mu_f"] == 1 and src["params"]["dt"] == 0.1 and src["params"]["save_deg"] == 2
+    S = ho.SurfaceStress(src["xyz"], src["tets"], mu=src["params"]["mu_f"], order=2)
+    assert (S.nF, len(S.maps.wall_cells), int((S.maps.n_ext == 2).sum())) == (1676, 1623, 53)
+    u = np.concatenate([1.0 - pts[:, 1] ** 2 - pts[:, 2] ** 2, np.zeros(2 * n)])
+    res = ho.run_time_loop(S, [u] * 9, src["params"]["dt"], (0, n, 2 * n))
+    fin = ho.finalize(res["wss_sum"], res["tawss_sum"], res["twssg_sum"], res["count"])
+    fx = src["xyz"][S.maps.facets][:, :, 0]
+    wall = (fx > 0.1).all(axis=1) & (fx < 4.9).all(axis=1)
+    avg = float((fin["TAWSS"].mean(axis=1) * S.area)[wall].sum() / S.area[wall].sum())
+    assert 1.95 < avg < 2.05
+    assert abs(avg - 1.99490423) < 1e-7          # SURVEY.md §8c probe value
+    ho.check_osi(fin["OSI"])
+    assert np.abs(fin["OSI"]).max() < 1e-12 and np.abs(fin["ECAP"]).max() < 1e-11
+    assert np.allclose(fin["RRT"], 1.0 / fin["TAWSS"], rtol=1e-12)
+    # steady flow: only the first step (tau_prev = 0, :244) contributes to TWSSG
+    tau = S(u, (0, n, 2 * n))
+    assert np.allclose(fin["TWSSG"], ho.project_dg_norm(tau / 0.1, S.area) / 9, rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("name", ["cylinder", "stenosis", "aneurysm"])
+def test_facet_order_matches_dolfin_written_boundaries(name):
+    """R1 golden vector: exterior facets in the order dolfin itself numbered them (/boundaries mesh function)."""
+    d = np.load(GOLDEN / "dolfin_facets.npz")
+    facets, cell, local = ho.exterior_facets(d[f"{name}_tets"])
+    assert np.array_equal(facets, d[f"{name}_exterior_in_dolfin_order"])
+    t = ho.order_cells(d[f"{name}_tets"])
+    for k in range(4):
+        sel = local == k
+        assert np.array_equal(np.delete(t[cell[sel]], k, axis=1), facets[sel])
+
+
+def test_quadratic_field_is_differentiated_exactly():
+    """§8c-3: a global quadratic velocity is in P2, so tau on single-facet cells equals the analytic traction."""
+    src = H.load_fluid("aneurysm")
+    xyz, tets = src["xyz"], src["tets"]
+    cn, edges = ho.p2_cell_nodes(tets)
+    pts = ho.p2_node_coordinates(xyz, edges)
+    rng = np.random.default_rng(1)
+    a, B, Cq = rng.normal(size=3), rng.normal(size=(3, 3)), rng.normal(size=(3, 3, 3))
+    Cq = 0.5 * (Cq + Cq.transpose(0, 2, 1))
+    L = np.ptp(xyz, axis=0).max()
+    x = (pts - xyz.mean(axis=0)) / L
+    u = a + x @ B.T + np.einsum("ijk,nj,nk->ni", Cq, x, x)
+    n = len(pts)
+    mu = 0.7
+    S = ho.SurfaceStress(xyz, tets, mu, 2)
+    tau = S(np.concatenate([u[:, 0], u[:, 1], u[:, 2]]), (0, n, 2 * n))
+    xv = (xyz[S.maps.bcell_parent] - xyz.mean(axis=0)) / L                    # (nF,3,3)
+    G = (B[None, None] + 2 * np.einsum("ijk,fvk->fvij", Cq, xv)) / L
+    sig = mu * (G + np.swapaxes(G, 2, 3))
+    nrm = S.normal[:, None, :]
+    F = -np.einsum("fvij,fvj->fvi", sig, np.broadcast_to(nrm, xv.shape))
+    Ft = F - np.einsum("fvi,fvi->fv", F, np.broadcast_to(nrm, F.shape))[..., None] * nrm
+    single = S.maps.n_ext[S.facet_wall] == 1
+    assert single.sum() > 700
+    assert np.abs(tau[single] - Ft[single]).max() < 1e-10 * np.abs(Ft).max()
+
+
+def test_rigid_rotation_and_reversal():
+    src = H.load_fluid("cylinder")
+    xyz, tets = src["xyz"], src["tets"]
+    cn, edges = ho.p2_cell_nodes(tets)
+    pts = ho.p2_node_coordinates(xyz, edges)
+    n = len(pts)
+    S = ho.SurfaceStress(xyz, tets, 1.0, 2)
+    ur = np.cross(np.array([0.3, -0.2, 0.5]), pts)
+    tau = S(np.concatenate([ur[:, 0], ur[:, 1], ur[:, 2]]), (0, n, 2 * n))
+    assert np.abs(tau).max() < 1e-9 * np.abs(ur).max() / np.ptp(pts, axis=0).max()
+    # pure reversal: mean WSS = 0 for an even count => OSI = 0.5 exactly, RRT = inf (compute_hemodynamics.py:344-345)
+    u0 = synth.velocity_series(synth.velocity_basis(pts, seed=2), np.array([[1.0, 0.2, 0.1, 0.3]]))[0]
+    res = ho.run_time_loop(S, [u0, -u0, u0, -u0], 0.1, (0, n, 2 * n))
+    fin = ho.finalize(res["wss_sum"], res["tawss_sum"], res["twssg_sum"], res["count"])
+    assert np.all(fin["OSI"] == 0.5) and np.all(np.isinf(fin["RRT"]))
+    with pytest.raises(AssertionError):   # the reference's own assertion demands min(OSI) < 0.5 (:371)
+        ho.check_osi(fin["OSI"])
+
+
+def test_multi_facet_cells_solve_the_dense_block_system():
+    """§8c-5: for a cell with two exterior facets, re-assemble A and b densely with a different exact rule
+    (6-point degree-4) and compare with the oracle's tau."""
+    src = H.load_pipe()
+    xyz, tets = src["xyz"], src["tets"]
+    cn, edges = ho.p2_cell_nodes(tets)
+    pts = ho.p2_node_coordinates(xyz, edges)
+    n = len(pts)
+    S = ho.SurfaceStress(xyz, tets, 1.3, 2)
+    u = synth.velocity_series(synth.velocity_basis(pts, seed=4), np.array([[1.0, 0.5, -0.3, 0.2]]))[0]
+    tau = S(u, (0, n, 2 * n))
+    # degree-4 Strang-Fix rule
+    a1, a2 = 0.816847572980459, 0.091576213509771
+    b1, b2 = 0.108103018168070, 0.445948490915965
+    pts4 = np.array([[a1, a2, a2], [a2, a1, a2], [a2, a2, a1], [b1, b2, b2], [b2, b1, b2], [b2, b2, b1]])
+    wts4 = np.array([0.109951743655322] * 3 + [0.223381589678011] * 3)
+    multi_cells = np.nonzero(S.maps.n_ext == 2)[0][:10]
+    t = ho.order_cells(tets)
+    for w in multi_cells:
+        fs = np.nonzero(S.facet_wall == w)[0]
+        A, b = np.zeros((4, 4)), np.zeros((4, 3))
+        cell = S.maps.wall_cells[w]
+        ucell = np.stack([u[c * n + cn[cell]] for c in range(3)], axis=-1)
+        for f in fs:
+            for q in range(6):
+                lam = np.zeros(4)
+                lam[S.facet_lv[f]] = pts4[q]
+                gphi = ho._p2_basis_gradients(lam, S.glam[w])
+                G = ucell.T @ gphi
+                F = -(S.mu * (G + G.T)) @ S.normal[f]
+                Ft = F - (F @ S.normal[f]) * S.normal[f]
+                A += wts4[q] * S.area[f] * np.outer(lam, lam)
+                b += wts4[q] * S.area[f] * np.outer(lam, Ft)
+        xsol = np.linalg.solve(A, b)
+        for f in fs:
+            assert np.allclose(tau[f], xsol[S.maps.bcell_local[f].astype(int)], rtol=1e-11, atol=1e-13)
+        assert t[cell].shape == (4,)
+
+
+@pytest.mark.parametrize("order", [2, 1])
+def test_c_twin_matches_numpy_restatement(order):
+    src = H.load_fluid("stenosis")
+    case = H.make_case(src["xyz"], src["tets"], order, n_snap=11)
+    S, res, _ = H.oracle_run(case, 3.5e-3, keep_wss=True)
+    n = case["n_nodes"]
+    co = c_oracle.COracle(S)
+    for threads in (1, 3):
+        r = co.run(case["u"], case["dt"], (0, n, 2 * n), keep_wss=True, threads=threads)
+        for k in ("wss_sum", "tawss_sum", "twssg_sum", "tau_last", "wss"):
+            assert H.rel_l2(r[k], res[k]) < 1e-13, (k, threads)
+    # continuation with an explicit tau_prev
+    r1 = co.run(case["u"][:5], case["dt"], (0, n, 2 * n))
+    r2 = co.run(case["u"][5:], case["dt"], (0, n, 2 * n), tau_prev=r1["tau_last"])
+    assert H.rel_l2(r1["twssg_sum"] + r2["twssg_sum"], res["twssg_sum"]) < 1e-13

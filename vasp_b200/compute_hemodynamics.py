@@ -1,0 +1,314 @@
+"""Drop-in for VaSP's ``vasp-compute-hemo`` / ``compute_hemodyanamics()`` with the numerics on a B200.
+
+Mirrors ``src/vasp/postprocessing/postprocessing_fenics/compute_hemodynamics.py`` of the reference: same function
+name (misspelling included) and signature (``:160-161``), same command-line flags
+(``postprocessing_fenics_common.py:17-28``), same input files (``<stem>_fluid.h5``, ``<stem>_refined_fluid.h5``,
+``Visualization_separate_domain/u.h5``, ``Checkpoint/default_variables.json``), same outputs
+(``Hemodynamic_indices/{RRT,OSI,ECAP,WSS,TAWSS,TWSSG}.xdmf|.h5``), same stdout progress lines and the same error
+conventions (``AssertionError`` for missing inputs / ``save_deg``, ``RuntimeError`` for unreadable parameters, the OSI
+range assertion after the files are written, ``:366-372``).
+
+What changed underneath: dolfin's per-snapshot assemble + LU + Python dof matching is replaced by the CUDA engine
+(:mod:`vasp_b200.engine`); snapshots are ``pread`` from ``u.h5`` into pinned buffers by a reader thread while the
+GPU works on the previous block; under a launcher (one process per GPU, torchrun-style ``RANK``/``WORLD_SIZE``)
+every rank takes a contiguous time range and the partial sums meet in one NCCL all-reduce.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import logging
+import threading
+import time
+from pathlib import Path
+from typing import Dict, Optional, Union
+
+import numpy as np
+
+from . import io_dolfin
+from .engine import HemoEngine, pinned_empty
+from .timeshard import NcclComm, env_rank_world, plan_shard
+
+INDEX_NAMES = ["RRT", "OSI", "ECAP", "WSS", "TAWSS", "TWSSG"]  # compute_hemodynamics.py:253
+
+
+def parse_arguments(argv=None) -> argparse.Namespace:
+    """The reference's flag set (``postprocessing_fenics_common.py:10-28``) plus two extensions that default to the
+    reference behaviour."""
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--folder", type=Path, help="Path to simulation results")
+    parser.add_argument('--mesh-path', type=Path, default=None,
+                        help="Path to the mesh file (default: <folder_path>/Mesh/mesh.h5)")
+    parser.add_argument("--stride", type=int, default=1, help="Save frequency of simulation")
+    parser.add_argument("-st", "--start-time", type=float, default=None, help="Desired start time for postprocessing")
+    parser.add_argument("-et", "--end-time", type=float, default=None, help="Desired end time for postprocessing")
+    parser.add_argument("--extract-entire-domain", action="store_true", help="Extract displacement from entire domain")
+    parser.add_argument("--log-level", type=int, default=20,
+                        help="Specify the log level (default is 20, which is INFO)")
+    # extensions
+    parser.add_argument("--velocity-degree", type=int, choices=[1, 2], default=2,
+                        help="2 (reference behaviour: P1 data on the refined mesh = P2 on the mesh) or 1 (P1 data on "
+                             "the un-refined mesh; the reference refuses save_deg != 2)")
+    parser.add_argument("--device", type=int, default=None, help="CUDA device (default: LOCAL_RANK)")
+    return parser.parse_args(argv)
+
+
+def read_parameters_from_file(folder: Union[str, Path]) -> Optional[Dict]:
+    """``postprocessing_common.py:124-145``."""
+    file_path = Path(folder) / "Checkpoint" / "default_variables.json"
+    try:
+        with open(file_path, 'r') as json_file:
+            return json.load(json_file)
+    except FileNotFoundError:
+        logging.error(f"File not found: {file_path}")
+        return None
+    except json.JSONDecodeError as e:
+        logging.error(f"Error parsing JSON file: {e}")
+        return None
+
+
+class _BlockReader:
+    """Reads snapshot blocks of ``u.h5`` into two pinned buffers, one block ahead of the consumer."""
+
+    def __init__(self, series: io_dolfin.VelocitySeries, first: int, last: int, block: int):
+        self.series, self.block = series, max(2, block)
+        self.ranges = []
+        pos = first
+        while pos < last:
+            end = min(pos + self.block, last)
+            if last - end == 1:  # never leave a single trailing snapshot (halo blocks need two)
+                end = last
+            self.ranges.append((pos, end))
+            pos = end
+        rows = max((b - a for a, b in self.ranges), default=1)
+        self.bufs = [pinned_empty((rows, series.vec_len)) for _ in range(2)]
+        self.io_seconds = 0.0
+        self._ready = [threading.Event(), threading.Event()]
+        self._free = [threading.Event(), threading.Event()]
+        for e in self._free:
+            e.set()
+        self._error: Optional[BaseException] = None
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _run(self) -> None:
+        try:
+            for i, (a, b) in enumerate(self.ranges):
+                slot = i & 1
+                self._free[slot].wait()
+                self._free[slot].clear()
+                t0 = time.perf_counter()
+                self.series.read_into(self.bufs[slot], a, b)
+                self.io_seconds += time.perf_counter() - t0
+                self._ready[slot].set()
+        except BaseException as e:  # surfaced in the consumer
+            self._error = e
+            for e2 in self._ready:
+                e2.set()
+
+    def __iter__(self):
+        for i, (a, b) in enumerate(self.ranges):
+            slot = i & 1
+            self._ready[slot].wait()
+            self._ready[slot].clear()
+            if self._error is not None:
+                raise self._error
+            yield a, b, self.bufs[slot][:b - a]
+            self._free[slot].set()
+
+
+def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path: Path,
+                          mu_f: float, stride: int = 1, velocity_degree: int = 2,
+                          device: Optional[int] = None, block_snapshots: Optional[int] = None) -> None:
+    """
+    Compute hemodynamic indices from velocity field (reference ``compute_hemodynamics.py:160-372``).
+
+    Args:
+        visualization_separate_domain_folder (Path): Path to the folder containing u.h5
+        mesh_path (Path): Path to the mesh folder
+        mu_f (float): Dynamic viscosity
+        stride (int): Save frequency of output data
+    """
+    rank, local_rank, world = env_rank_world()
+    visualization_separate_domain_folder = Path(visualization_separate_domain_folder)
+    mesh_path = Path(mesh_path)
+    file_path_u = visualization_separate_domain_folder / "u.h5"
+    assert file_path_u.exists(), f"Velocity file {file_path_u} not found.  Make sure to run create_hdf5.py first."
+    t_begin = time.perf_counter()
+    series = io_dolfin.VelocitySeries(file_path_u, "velocity", stride)
+
+    if rank == 0:
+        print("--- Read the original mesh and also the refined mesh \n")
+    mesh_name = mesh_path.stem
+    fluid_mesh_path = mesh_path.parent / f"{mesh_name}_fluid.h5"
+    assert fluid_mesh_path.exists(), f"Mesh file {fluid_mesh_path} not found."
+    xyz, tets = io_dolfin.read_mesh(fluid_mesh_path, "mesh")
+
+    eng = HemoEngine(local_rank if device is None else device)
+    eng.set_mesh(xyz, tets)  # BoundaryMesh(mesh, "exterior") and all index maps, on the device
+
+    if rank == 0:
+        print("--- Define function spaces \n")
+    if velocity_degree == 2:
+        refined_mesh_path = mesh_path.parent / f"{mesh_name}_refined_fluid.h5"
+        assert refined_mesh_path.exists(), f"Mesh file {refined_mesh_path} not found."
+        rxyz, rtets = io_dolfin.read_mesh(refined_mesh_path, "mesh")
+        comp_offset, node_stride, perm = series.layout(rtets, len(rxyz))
+        eng.set_velocity_layout(2, refined_xyz=rxyz, node_perm=perm, comp_offset=comp_offset, node_stride=node_stride)
+    else:
+        comp_offset, node_stride, perm = series.layout(tets, len(xyz))
+        eng.set_velocity_layout(1, n_nodes=len(xyz), node_perm=perm, comp_offset=comp_offset, node_stride=node_stride)
+    if rank == 0:
+        print("--- Define functions")
+
+    maps = eng.maps()
+    hemodynamic_indices_path = visualization_separate_domain_folder.parent / "Hemodynamic_indices"
+    hemodynamic_indices_path.mkdir(parents=True, exist_ok=True)
+    bgeom = xyz[maps["bvert_parent"]]
+
+    if rank == 0:
+        print("=" * 10, "Start post processing", "=" * 10)
+
+    n_snap = len(series)
+    assert n_snap >= 2, "at least two snapshots are needed (dt is the gap between the first two)"
+    # Get time difference between two consecutive time steps
+    dt = float(series.timestamps[1] - series.timestamps[0])
+    eng.begin(mu_f, dt)
+    comm = NcclComm(eng, rank, world) if world > 1 else None
+
+    shard = plan_shard(n_snap, rank, world)
+    nF = eng.nF
+    if block_snapshots is None:
+        # ~256 MiB of pinned memory per buffer, at least 2 and at most 512 snapshots
+        block_snapshots = int(min(512, max(2, (256 << 20) // (series.vec_len * 8))))
+    eng.set_tuning(batch_snapshots=block_snapshots, chunk_snapshots=0)
+
+    wss_writer = None
+    shard_file = None
+    if rank == 0:
+        wss_writer = io_dolfin.CheckpointWriter(hemodynamic_indices_path, "WSS", maps["btopology"], bgeom, True)
+    elif shard.count:
+        shard_file = np.lib.format.open_memmap(hemodynamic_indices_path / f".WSS_shard{rank}.npy", mode="w+",
+                                               dtype=np.float64, shape=(shard.count, nF, 3, 3))
+    wss_buf = pinned_empty((block_snapshots + 1, nF, 3, 3))
+
+    reader = _BlockReader(series, shard.read_start, shard.stop, block_snapshots)
+    first, done = True, 0
+    for a, b, u in reader:
+        flags = shard.first_push_flags() if first else 0
+        n_real = (b - a) - (1 if (first and shard.has_halo) else 0)
+        eng.push(u, flags=flags, wss_out=wss_buf)
+        for r in range(n_real):
+            k = shard.start + done + r
+            t = float(series.timestamps[k])
+            if rank == 0:
+                print("=" * 10, f"Calculating WSS at Timestep: {t}", "=" * 10)
+                # Write temporal WSS
+                wss_writer.write(wss_buf[r], t)
+            else:
+                shard_file[done + r] = wss_buf[r]
+        done += n_real
+        first = False
+    series_io = reader.io_seconds
+    if shard_file is not None:
+        shard_file.flush()
+        del shard_file
+    if comm is not None:
+        comm.allreduce_sums()  # the single collective: 15*nF partial sums + the snapshot count
+
+    if rank == 0:
+        # WSS of the other ranks' time ranges, in order
+        for r in range(1, world):
+            sh = plan_shard(n_snap, r, world)
+            part = hemodynamic_indices_path / f".WSS_shard{r}.npy"
+            if sh.count:
+                arr = np.load(part, mmap_mode="r")
+                for i in range(sh.count):
+                    wss_writer.write(arr[i], float(series.timestamps[sh.start + i]))
+                del arr
+                part.unlink()
+        wss_writer.close()
+        print("=" * 10, "Saving hemodynamic indices", "=" * 10)
+
+    out = eng.finalize(n_snap)
+    timers = eng.timers()
+    series.close()
+    if rank == 0:
+        # Write indices to file
+        for name in INDEX_NAMES:
+            if name == "WSS":
+                continue
+            w = io_dolfin.CheckpointWriter(hemodynamic_indices_path, name, maps["btopology"], bgeom, False)
+            w.write(out[name], 0)
+            w.close()
+            print(f"--- {name} is saved in {hemodynamic_indices_path}")
+        total = time.perf_counter() - t_begin
+        print(f"--- timing: total {total:.3f} s | u.h5 -> pinned host {series_io:.3f} s | host -> device "
+              f"{timers['h2d_ms'] * 1e-3:.3f} s | kernels {timers['kernel_ms'] * 1e-3:.3f} s | "
+              f"{nF} wall facets x {n_snap} snapshots on {world} GPU(s)")
+    eng.close()
+
+    if rank == 0:
+        # assert that OSI is within 0 to 0.5
+        min_, max_ = np.min(out["OSI"]), np.max(out["OSI"])
+        tol = 1e-12
+        assert -tol <= min_ < 0.5, "OSI min is not within 0 to 0.5"
+        assert -tol < max_ <= 0.5 + tol, "OSI max is not within 0 to 0.5"
+
+
+# correctly spelt alias
+compute_hemodynamics = compute_hemodyanamics
+
+
+def main(argv=None) -> None:
+    rank, _, world = env_rank_world()
+    if world == 1:
+        print("--- Running in serial mode, you can use MPI to speed up the postprocessing. \n")
+
+    args = parse_arguments(argv)
+    folder_path = Path(args.folder)
+
+    assert folder_path.exists(), f"Folder {folder_path} not found."
+
+    visualization_separate_domain_folder = folder_path / "Visualization_separate_domain"
+    parameters = read_parameters_from_file(args.folder)
+    if parameters is None:
+        raise RuntimeError("Error reading parameters from file.")
+
+    if visualization_separate_domain_folder.exists():
+        if rank == 0:
+            print("--- Visualization_separate_domain folder found \n")
+    else:
+        if rank == 0:
+            print("--- Visualization_separate_domain folder not found \n")
+        # The reference falls back to create_hdf5() here (compute_hemodynamics.py:389-431); that converter is the
+        # producer of this path's input and is not part of it.
+        raise AssertionError(f"{visualization_separate_domain_folder} not found.  Run vasp-create-hdf5 first.")
+
+    save_deg = parameters["save_deg"]
+    if args.velocity_degree == 2:
+        assert save_deg == 2, "This script only works for save_deg = 2"
+    mu_f = parameters["mu_f"]
+
+    if isinstance(mu_f, list):
+        if rank == 0:
+            print("--- two fluid regions are detected. Using the first fluid region for viscosity \n")
+        mu_f = mu_f[0]
+
+    if args.mesh_path:
+        mesh_path = Path(args.mesh_path)
+        if rank == 0:
+            print("--- Using user-defined mesh \n")
+        assert mesh_path.exists(), f"Mesh file {mesh_path} not found."
+    else:
+        mesh_path = folder_path / "Mesh" / "mesh.h5"
+        if rank == 0:
+            print("--- Using mesh from default turrtleFSI Mesh folder \n")
+        assert mesh_path.exists(), f"Mesh file {mesh_path} not found."
+
+    compute_hemodyanamics(visualization_separate_domain_folder, mesh_path, mu_f, args.stride,
+                          velocity_degree=args.velocity_degree, device=args.device)
+
+
+if __name__ == "__main__":
+    main()

@@ -379,7 +379,7 @@ def _space_msg(shape: Tuple[int, ...]) -> bytes:
 def _attr_msg(name: str, value) -> bytes:
     if isinstance(value, (str, bytes)):
         raw = value.encode() if isinstance(value, str) else value
-        arr = np.array(raw + b"\0", dtype=f"S{len(raw) + 1}")
+        arr = np.array(raw, dtype=f"S{max(len(raw), 1)}")  # dolfin stores the exact length, no terminator
     else:
         arr = np.asarray(value)
         if arr.dtype.kind == "f":
