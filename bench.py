@@ -235,9 +235,9 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         eng.sync()
     if comm:
         comm.barrier()
-    k2_ms, k2_n = eng.kernel_profile()
+    k1_ms, k2_ms, k2_n = eng.kernel_profile()
     eng.set_profile(False)
-    launches = eng.timers()["launches"] - launches0  # k2 + k3 + k4 per step (the untimed L2 flush is not counted)
+    launches = eng.timers()["launches"] - launches0  # k1 + k2 (+ k2 multi) + k3 + k4 per step (L2 flush not counted)
     total_ms = float(np.sum(step_ms))
     if comm:
         total_ms = comm.max(total_ms)
@@ -270,7 +270,11 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     b_alg = algorithmic_bytes_per_unit(order)
     units_per_launch = nF * n_snap
     k2_avg_ms = k2_ms / max(k2_n, 1)
+    k1_avg_ms = k1_ms / max(k2_n, 1)
+    units_per_launch = units_per_launch * args.steps // max(k2_n, 1)  # a step may split into several column blocks
     achieved = units_per_launch * b_alg / (k2_avg_ms * 1e-3) / 1e9
+    # K1 (staging) moves 8 B x 3 components per wall-layer node and snapshot, read once and written once
+    k1_bytes = 2 * 24 * eng.n_wall_nodes * (n_snap + halo) * args.steps / max(k2_n, 1)
     traffic = None
     tfile = ROOT / "profiles" / "k2_traffic.json"  # written from an `ncu --set full` capture of this command
     if tfile.exists():
@@ -286,17 +290,23 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {wl['desc']}", "facets": nF, "snapshots_per_gpu": n_snap,
-                   "order": order, "velocity_nodes": int(len(wl["points"])), "tets": int(len(wl["tets"])),
+                   "order": order, "velocity_nodes": int(len(wl["points"])), "wall_layer_nodes": eng.n_wall_nodes,
+                   "tets": int(len(wl["tets"])),
                    "parallelism": f"time-shard x{world}", "l2": "flushed between timed steps (512 MiB write)",
                    "results_sane": sane},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": f"k2_traction<{order}>", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": f"k2_wall<{order}>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_unit": b_alg, "units_per_launch": units_per_launch,
-                     "kernel_ms_per_launch": k2_avg_ms, "launches_timed": k2_n},
+                     "kernel_ms_per_launch": k2_avg_ms, "launches_timed": k2_n,
+                     "stage_kernel": {"kernel": "k1_stage", "ms_per_launch": k1_avg_ms,
+                                      "bytes_per_launch": k1_bytes,
+                                      "achieved": k1_bytes / (k1_avg_ms * 1e-3) / 1e9 if k1_avg_ms > 0 else None,
+                                      "frac": k1_bytes / (k1_avg_ms * 1e-3) / 1e9 / peak if k1_avg_ms > 0 else None,
+                                      "wall_nodes": eng.n_wall_nodes}},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

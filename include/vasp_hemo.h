@@ -65,8 +65,9 @@ int vh_set_velocity_layout(vh_handle* h, int order, const double* refined_xyz, i
                            const int64_t* node_perm, const int64_t comp_offset[3], int64_t node_stride);
 
 /* Sizes of what K0 produced: n[0]=nF exterior facets, n[1]=nBV boundary vertices, n[2]=wall cells,
- * n[3]=facets in cells with >=2 exterior facets, n[4]=dofs per cell (4|10), n[5]=velocity nodes. */
-int vh_get_sizes(vh_handle* h, int64_t n[6]);
+ * n[3]=facets in cells with >=2 exterior facets, n[4]=dofs per cell (4|10), n[5]=velocity nodes,
+ * n[6]=wall-layer velocity nodes (nodes of cells that own an exterior facet; what K1 stages per snapshot). */
+int vh_get_sizes(vh_handle* h, int64_t n[7]);
 
 /* Index maps for bit-exact checks against the oracle and for the output writer (any pointer may be NULL):
  *   facet_cell[nF], facet_local[nF] (face opposite local vertex k), facet_verts[nF*3] ascending parent vertex ids,
@@ -84,8 +85,8 @@ int vh_get_geometry(vh_handle* h, double* normal, double* area, double* glam);
  * Also zeroes the running sums (a new time loop). */
 int vh_begin(vh_handle* h, double mu, double dt);
 
-/* Tuning: max snapshots resident per device batch (0 = auto from free memory), snapshots per thread chunk
- * (0 = auto so that the grid fills 148 SMs). */
+/* Tuning: max snapshots per host->device batch (0 = auto from free memory), snapshots per time segment of the
+ * K2 grid (0 = auto so that the grid fills 148 SMs). */
 int vh_set_tuning(vh_handle* h, int64_t batch_snapshots, int64_t chunk_snapshots);
 
 /* ---- snapshot loop (K2/K3) -------------------------------------------------------------------------------
@@ -117,10 +118,11 @@ int vh_finalize(vh_handle* h, int64_t n_total, double* tawss, double* osi, doubl
 int vh_sync(vh_handle* h);
 /* Milliseconds spent in kernels / in H2D copies since vh_begin (CUDA events), and number of kernel launches. */
 int vh_get_timers(vh_handle* h, double* kernel_ms, double* h2d_ms, int64_t* launches);
-/* Per-launch CUDA-event timing of the dominant kernel (k2_traction), for the roofline: switch on, run, then read
- * the summed duration and launch count since the last read (reading synchronises and resets). */
+/* Per-launch CUDA-event timing of the two hot kernels, for the roofline: switch on, run, then read the summed
+ * durations of k1_stage (wall-layer staging) and k2_wall (traction + reductions) and the number of launches of each
+ * since the last read (reading synchronises and resets). */
 int vh_set_profile(vh_handle* h, int on);
-int vh_get_kernel_profile(vh_handle* h, double* k2_ms, int64_t* k2_launches);
+int vh_get_kernel_profile(vh_handle* h, double* k1_ms, double* k2_ms, int64_t* launches);
 /* Start/stop markers on the compute stream (CUDA events); stop synchronises and returns the elapsed ms. */
 int vh_timer_start(vh_handle* h);
 int vh_timer_stop(vh_handle* h, double* ms);

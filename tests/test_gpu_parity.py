@@ -82,6 +82,42 @@ def test_chunking_batching_and_halo_are_equivalent(engine_lib, order):
     a.close(), b.close()
 
 
+@pytest.mark.parametrize("order", [2, 1])
+def test_segments_passes_and_column_blocks(engine_lib, order):
+    """100 snapshots: several 31-column lane passes per segment, several segments, several staged column blocks
+    (device-resident push), per-step WSS and tau_last all agree with the sequential oracle."""
+    src = H.load_fluid("cylinder")
+    case = H.make_case(src["xyz"], src["tets"], order, n_snap=100)
+    mu = 2.0
+    _, res, fin = H.oracle_run(case, mu, keep_wss=True)
+    u = np.ascontiguousarray(case["u"])
+    for batch, chunk in ((0, 0), (0, 31), (0, 62), (40, 0), (33, 93)):
+        eng = H.engine_for(case, mu)
+        eng.set_tuning(batch, chunk)
+        d_u = eng.device_alloc(u.nbytes)
+        eng.h2d(d_u, u)
+        nF = eng.nF
+        d_w = eng.device_alloc(100 * nF * 72)
+        eng.push_device(d_u, 100, u.shape[1] * 8, flags=1, d_wss=d_w)
+        wss = np.empty((100, nF, 3, 3))
+        eng.d2h(wss, d_w)
+        assert H.rel_l2(wss, res["wss"]) < TOL, (batch, chunk)
+        out = eng.finalize()
+        for name in H.FIELDS:
+            assert H.rel_l2(out[name], fin[name]) < TOL, (name, batch, chunk)
+        assert H.rel_l2(eng.tau_last(), res["tau_last"]) < TOL
+        # the same through the host path, split in two pushes with a halo start
+        eng.begin(mu, case["dt"])
+        eng.push(u[:37], flags=1)
+        eng.push(u[37:])
+        out = eng.finalize()
+        for name in H.FIELDS:
+            assert H.rel_l2(out[name], fin[name]) < TOL, (name, batch, chunk, "host")
+        eng.device_free(d_u)
+        eng.device_free(d_w)
+        eng.close()
+
+
 def test_poiseuille_known_answer(engine_lib):
     """The reference's own pin (tests/test_compute_hemodynamics.py:68-88): wall-averaged TAWSS in (1.95, 2.05) for
     G=4, mu=1, R=1, and OSI within [-1e-12, 0.5 + 1e-12]."""

@@ -46,7 +46,7 @@ _SIGNATURES = {
     "vh_sync": [_P],
     "vh_get_timers": [_P, C.POINTER(_DBL), C.POINTER(_DBL), C.POINTER(_I64)],
     "vh_set_profile": [_P, C.c_int],
-    "vh_get_kernel_profile": [_P, C.POINTER(_DBL), C.POINTER(_I64)],
+    "vh_get_kernel_profile": [_P, C.POINTER(_DBL), C.POINTER(_DBL), C.POINTER(_I64)],
     "vh_timer_start": [_P],
     "vh_timer_stop": [_P, C.POINTER(_DBL)],
     "vh_alloc_pinned": [C.POINTER(_P), _I64],

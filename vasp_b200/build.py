@@ -13,7 +13,7 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
-SOURCES = ["abi.cu", "k0_precompute.cu", "k2_traction.cu"]
+SOURCES = ["abi.cu", "k0_precompute.cu", "k1_stage.cu", "k2_wall.cu"]
 OUT = HERE / "libvasp_hemo.so"
 
 NVCC_FLAGS = [

@@ -1,6 +1,6 @@
 // extern "C" surface of libvasp_hemo.so (include/vasp_hemo.h): handle lifetime, double-buffered snapshot staging,
 // result export and the dlopen'ed NCCL reduction.  No torch, no CPU compute path: every numeric result comes from the
-// kernels in k0_precompute.cu / k2_traction.cu.
+// kernels in k0_precompute.cu / k1_stage.cu / k2_wall.cu.
 #include <dlfcn.h>
 #include <nccl.h>  // types only; the library is resolved at run time
 #include <stdarg.h>
@@ -130,7 +130,7 @@ int vh_destroy(vh_handle* h) {
     k_free_run_buffers(h);
     void* ptrs[] = {h->d_xyz, h->d_tets, h->d_facet_cell, h->d_facet_verts, h->d_bcell_parent, h->d_btopology,
                     h->d_bvert_parent, h->d_facet_local, h->d_bcell_local, h->d_blocal_soa, h->d_glam, h->d_normal,
-                    h->d_area, h->d_work, h->d_m_lf, h->d_m_w, h->d_facet_nodes, h->d_slot, h->d_flush, h->d_scalar};
+                    h->d_area, h->d_work, h->d_m_lf, h->d_m_w, h->d_facet_nodes, h->d_row, h->d_wall_slot, h->d_flush, h->d_scalar};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 2; ++i) {
@@ -172,9 +172,10 @@ int vh_set_velocity_layout(vh_handle* h, int order, const double* refined_xyz, i
     return k0_build_velocity_map(h, order, refined_xyz, n_nodes, tol, node_perm);
 }
 
-int vh_get_sizes(vh_handle* h, int64_t n[6]) {
+int vh_get_sizes(vh_handle* h, int64_t n[7]) {
     VH_CHECK(h && n, VH_ERR_ARG, "vh_get_sizes: null argument");
     n[0] = h->nF; n[1] = h->nBV; n[2] = h->nW; n[3] = h->nMulti; n[4] = h->ndof; n[5] = h->n_nodes;
+    n[6] = h->order ? h->nWn : 0;
     return VH_OK;
 }
 
@@ -249,6 +250,9 @@ int vh_set_tuning(vh_handle* h, int64_t batch_snapshots, int64_t chunk_snapshots
             h->d_stage[i] = h->d_wss_stage[i] = nullptr;
         }
         h->stage_cap = h->wss_stage_cap = 0;
+        if (h->d_W) cudaFree(h->d_W);  // the staged block is re-sized on the next launch
+        h->d_W = nullptr;
+        h->w_ld = 0;
     }
     h->batch_snapshots = batch_snapshots;
     h->chunk_snapshots = chunk_snapshots;
@@ -298,7 +302,9 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
     VH_CHECK(!halo || n_snap >= 2, VH_ERR_ARG, "halo push needs at least one real snapshot after the halo");
     const int64_t nF = h->nF;
 
-    // stage capacity: user value, else as many snapshots as fit in ~30 % of free memory / 2 buffers, capped at 8 GiB
+    // stage capacity: user value, else an eighth of the push (so that the copy of batch i+1 hides behind the kernels
+    // of batch i and only the last batch's kernels are exposed), at least 32 snapshots, at most what fits in ~30 %
+    // of free memory / 2 buffers or 8 GiB
     if (h->stage_cap == 0) {
         int64_t cap = h->batch_snapshots;
         if (cap <= 0) {
@@ -307,7 +313,9 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
             int64_t per_snap = vec_bytes + (wss_out ? 72 * nF : 0);
             int64_t budget = (int64_t)(0.3 * (double)free_b) / 2;
             if (budget > (8LL << 30)) budget = 8LL << 30;
-            cap = budget / per_snap;
+            cap = (n_snap + 7) / 8;
+            if (cap < 32) cap = 32;
+            if (cap > budget / per_snap) cap = budget / per_snap;
             if (cap > n_snap) cap = n_snap;
         }
         if (cap < 2) cap = 2;
@@ -466,7 +474,7 @@ int vh_set_profile(vh_handle* h, int on) {
     VH_CHECK(h, VH_ERR_ARG, "vh_set_profile: null handle");
     VH_CUDA(cudaSetDevice(h->device));
     if (on && h->prof_pool.empty()) {
-        h->prof_pool.resize(1024);
+        h->prof_pool.resize(3 * 512);
         for (auto& e : h->prof_pool) VH_CUDA(cudaEventCreate(&e));
     }
     h->profile = on != 0;
@@ -474,18 +482,21 @@ int vh_set_profile(vh_handle* h, int on) {
     return VH_OK;
 }
 
-int vh_get_kernel_profile(vh_handle* h, double* k2_ms, int64_t* k2_launches) {
+int vh_get_kernel_profile(vh_handle* h, double* k1_ms, double* k2_ms, int64_t* launches) {
     VH_CHECK(h, VH_ERR_ARG, "vh_get_kernel_profile: null handle");
     VH_CUDA(cudaSetDevice(h->device));
     VH_CUDA(cudaStreamSynchronize(h->s_compute));
-    double tot = 0.0;
-    for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+    double t1 = 0.0, t2 = 0.0;
+    for (size_t i = 0; i + 2 < h->prof_used; i += 3) {
         float ms = 0.f;
         VH_CUDA(cudaEventElapsedTime(&ms, h->prof_pool[i], h->prof_pool[i + 1]));
-        tot += ms;
+        t1 += ms;
+        VH_CUDA(cudaEventElapsedTime(&ms, h->prof_pool[i + 1], h->prof_pool[i + 2]));
+        t2 += ms;
     }
-    if (k2_ms) *k2_ms = tot;
-    if (k2_launches) *k2_launches = (int64_t)(h->prof_used / 2);
+    if (k1_ms) *k1_ms = t1;
+    if (k2_ms) *k2_ms = t2;
+    if (launches) *launches = (int64_t)(h->prof_used / 3);
     h->prof_used = 0;
     return VH_OK;
 }

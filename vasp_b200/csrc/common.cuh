@@ -41,11 +41,11 @@ constexpr int VH_MAX_CONTRIB = 4;  // a tet has at most 4 exterior facets
 // Per-facet constants in HBM, all SoA over facets (row r of an array with R rows: ptr[r * nF + f]).
 struct FacetTables {
     int64_t nF;
-    const int32_t* slot;   // [ndof][nF]  node_stride * node_perm[velocity node of cell dof k]
+    const int32_t* row;    // [ndof][nF]  wall-node number (row triple of the staged block W) of cell dof k
     const double* glam;    // [12][nF]    grad lambda_a (a-major, xyz minor), a in facet-canonical labels
     const double* normal;  // [3][nF]     outward unit normal
-    // work list: single-facet-cell facets first (padded to a warp multiple with -1), then facets whose cell owns
-    // >= 2 exterior facets; multi_start is warp aligned
+    // work list (one warp per entry): single-facet-cell facets first, then facets whose cell owns >= 2 exterior
+    // facets, starting at multi_start; -1 entries are padding
     const int32_t* work;
     int64_t n_work, multi_start;
     // multi-facet cells (SurfaceProjector's 4x4 blocks): per multi facet m = work index - multi_start
@@ -79,7 +79,13 @@ struct vh_handle {
     int64_t n_nodes = 0, vec_len = 0, node_stride = 1;
     int64_t comp_offset[3] = {0, 0, 0};
     int32_t* d_facet_nodes = nullptr;  // [ndof][nF] velocity node ids (map export)
-    int32_t* d_slot = nullptr;         // [ndof][nF]
+    int32_t* d_row = nullptr;          // [ndof][nF] wall-node number of each cell dof, facet-canonical dof order
+    // wall-layer nodes = velocity nodes referenced by any wall cell, ascending in vector position
+    int64_t nWn = 0, nWn_pad = 0;      // padded to a multiple of 32 (padding repeats the last node)
+    int32_t* d_wall_slot = nullptr;    // [nWn_pad] element offset of the node inside a snapshot vector
+    // K1 output: W[(3 * wall node + component) * w_ld + column], columns = snapshots of the current launch
+    double* d_W = nullptr;
+    int64_t w_ld = 0;                  // columns allocated per row (multiple of 32)
 
     // run state
     double mu = 0.0, dt = 0.0;
@@ -107,7 +113,8 @@ struct vh_handle {
     // timers
     double kernel_ms = 0.0, h2d_ms = 0.0;
     int64_t launches = 0;
-    // per-launch timing of the dominant kernel (k2_traction) for the roofline: event pairs from a pre-made pool
+    // per-launch timing of K1 (k1_stage) and K2 (k2_wall) for the roofline: event triples from a pre-made pool
+    // (before K1, between K1 and K2, after K2)
     bool profile = false;
     std::vector<cudaEvent_t> prof_pool;
     size_t prof_used = 0;
@@ -123,9 +130,14 @@ int k0_build_mesh(vh_handle* h, const double* xyz, int64_t nv, const int64_t* te
 int k0_build_velocity_map(vh_handle* h, int order, const double* refined_xyz, int64_t n_nodes, double tol,
                           const int64_t* node_perm);
 
-// ---- K2/K3/K4 (k2_traction.cu) ------------------------------------------------------------------------------------
-// One launch over `n_snap` resident snapshots (d_u + s * stride_elems).  prev_mode: 0 tau_prev=0, 1 tau_prev from
-// h->d_tau_last, 2 recompute from the snapshot just before d_u (halo).  d_wss (may be null): [n_snap][nF][9].
+// ---- K1 (k1_stage.cu) ------------------------------------------------------------------------------------------------
+// W[(3 i + c) * ld + col] = u[col * stride_elems + comp_offset[c] + wall_slot[i]] for col < ncol, i < nWn_pad
+int k1_launch(vh_handle* h, const double* d_u, int64_t ncol, int64_t stride_elems);
+
+// ---- K2/K3/K4 (k2_wall.cu) ---------------------------------------------------------------------------------------
+// `n_snap` resident snapshots (d_u + s * stride_elems), staged (K1) and reduced (K2, K3) in column blocks.
+// prev_mode: 0 tau_prev=0, 1 tau_prev from h->d_tau_last, 2 recompute from the snapshot just before d_u (halo).
+// d_wss (may be null): [n_snap][nF][9].
 int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_elems, int prev_mode, double* d_wss);
 int k4_finalize(vh_handle* h, int64_t n_total, double* d_out5);  // d_out5: 5 arrays [nF*3] TAWSS,OSI,RRT,ECAP,TWSSG
 int k_free_run_buffers(vh_handle* h);

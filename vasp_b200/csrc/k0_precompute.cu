@@ -478,15 +478,12 @@ __global__ void k0_p1_nodes(const int32_t* __restrict__ tets, int64_t nF, const 
     facet_nodes[idx] = tets[4 * (int64_t)facet_cell[f] + k];
 }
 
-// Gather slots in facet-canonical dof order: vertices (b0,b1,b2,opp), then edges e01,e02,e12,e03,e13,e23.
-// facet_nodes is in UFC cell order (4 vertices, edges (2,3),(1,3),(1,2),(0,3),(0,2),(0,1)).
-__global__ void k0_slots(const int32_t* __restrict__ facet_nodes, const int8_t* __restrict__ bcell_local,
-                         const int8_t* __restrict__ facet_local, const int64_t* __restrict__ perm, int64_t nF, int ndof,
-                         int64_t node_stride, int32_t* __restrict__ slot) {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nF * ndof) return;
-    int64_t f = idx % nF;
-    int kc = (int)(idx / nF);
+// Position (permuted velocity node) of facet-canonical cell dof kc: vertices (b0,b1,b2,opp), then edges
+// e01,e02,e12,e03,e13,e23.  facet_nodes is in UFC cell order (4 vertices, edges (2,3),(1,3),(1,2),(0,3),(0,2),(0,1)).
+__device__ __forceinline__ int64_t canonical_dof_node(const int32_t* __restrict__ facet_nodes,
+                                                      const int8_t* __restrict__ bcell_local,
+                                                      const int8_t* __restrict__ facet_local,
+                                                      const int64_t* __restrict__ perm, int64_t nF, int64_t f, int kc) {
     int nl[4] = {bcell_local[3 * f], bcell_local[3 * f + 1], bcell_local[3 * f + 2], facet_local[f]};
     int old;
     if (kc < 4) {
@@ -498,8 +495,41 @@ __global__ void k0_slots(const int32_t* __restrict__ facet_nodes, const int8_t* 
         old = 9 - (lo == 0 ? hi - 1 : lo == 1 ? hi + 1 : 5);
     }
     int64_t v = facet_nodes[(int64_t)old * nF + f];
-    if (perm) v = perm[v];
-    slot[idx] = (int32_t)(v * node_stride);
+    return perm ? perm[v] : v;
+}
+
+// wall-layer nodes: every velocity node some wall cell touches
+__global__ void k0_mark_wall_nodes(const int32_t* __restrict__ facet_nodes, const int8_t* __restrict__ bcell_local,
+                                   const int8_t* __restrict__ facet_local, const int64_t* __restrict__ perm, int64_t nF,
+                                   int ndof, int64_t n_nodes, int32_t* __restrict__ flag, int32_t* __restrict__ bad) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nF * ndof) return;
+    int64_t p = canonical_dof_node(facet_nodes, bcell_local, facet_local, perm, nF, idx % nF, (int)(idx / nF));
+    if (p < 0 || p >= n_nodes) {
+        atomicAdd(bad, 1);
+        return;
+    }
+    flag[p] = 1;
+}
+
+// wall_slot[i] = offset inside a snapshot vector of the i-th wall node (ascending => K1 reads are as coalesced as the
+// numbering allows); entries [nWn, nWn_pad) repeat the last node so that K1 needs no bounds checks
+__global__ void k0_wall_slots(const int32_t* __restrict__ flag, const int32_t* __restrict__ pos, int64_t n_nodes,
+                              int64_t node_stride, int64_t nWn, int64_t nWn_pad, int32_t* __restrict__ wall_slot) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_nodes || !flag[p]) return;
+    int32_t s = (int32_t)(p * node_stride);
+    wall_slot[pos[p]] = s;
+    if (pos[p] == nWn - 1)
+        for (int64_t i = nWn; i < nWn_pad; ++i) wall_slot[i] = s;
+}
+
+__global__ void k0_rows(const int32_t* __restrict__ facet_nodes, const int8_t* __restrict__ bcell_local,
+                        const int8_t* __restrict__ facet_local, const int64_t* __restrict__ perm,
+                        const int32_t* __restrict__ pos, int64_t nF, int ndof, int32_t* __restrict__ row) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nF * ndof) return;
+    row[idx] = pos[canonical_dof_node(facet_nodes, bcell_local, facet_local, perm, nF, idx % nF, (int)(idx / nF))];
 }
 
 template <typename T>
@@ -526,7 +556,7 @@ int k0_build_mesh(vh_handle* h, const double* xyz, int64_t nv, const int64_t* te
     dev_free(h->d_bcell_parent); dev_free(h->d_btopology); dev_free(h->d_bvert_parent); dev_free(h->d_facet_local);
     dev_free(h->d_bcell_local); dev_free(h->d_blocal_soa); dev_free(h->d_glam); dev_free(h->d_normal);
     dev_free(h->d_area); dev_free(h->d_work); dev_free(h->d_m_lf); dev_free(h->d_m_w);
-    dev_free(h->d_facet_nodes); dev_free(h->d_slot);
+    dev_free(h->d_facet_nodes); dev_free(h->d_row); dev_free(h->d_wall_slot);
     k_free_run_buffers(h);
     h->order = 0;
     h->nv = nv;
@@ -634,9 +664,10 @@ int k0_build_velocity_map(vh_handle* h, int order, const double* refined_xyz, in
     const int64_t nF = h->nF;
     const int ndof = order == 2 ? 10 : 4;
     dev_free(h->d_facet_nodes);
-    dev_free(h->d_slot);
+    dev_free(h->d_row);
+    dev_free(h->d_wall_slot);
     VH_TRY(dev_alloc(&h->d_facet_nodes, ndof * nF));
-    VH_TRY(dev_alloc(&h->d_slot, ndof * nF));
+    VH_TRY(dev_alloc(&h->d_row, ndof * nF));
     if (order == 1) {
         VH_CHECK(n_nodes == h->nv, VH_ERR_ARG, "vh_set_velocity_layout: order 1 needs n_nodes == nv (%lld != %lld)",
                  (long long)n_nodes, (long long)h->nv);
@@ -698,12 +729,35 @@ int k0_build_velocity_map(vh_handle* h, int order, const double* refined_xyz, in
         VH_TRY(dev_alloc(&d_perm, n_nodes));
         VH_CUDA(cudaMemcpyAsync(d_perm, node_perm, sizeof(int64_t) * n_nodes, cudaMemcpyHostToDevice, st));
     }
-    k0_slots<<<nblk(ndof * nF), TPB, 0, st>>>(h->d_facet_nodes, h->d_bcell_local, h->d_facet_local, d_perm, nF, ndof,
-                                              h->node_stride, h->d_slot);
+    // wall-layer node list (ascending vector position) and the per-facet row table K2 reads the staged block with
+    int32_t *d_flag = nullptr, *d_pos = nullptr, *d_cnt = nullptr;
+    VH_TRY(dev_alloc(&d_flag, n_nodes));
+    VH_TRY(dev_alloc(&d_pos, n_nodes));
+    VH_TRY(dev_alloc(&d_cnt, 2));
+    VH_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int32_t) * n_nodes, st));
+    VH_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int32_t) * 2, st));
+    k0_mark_wall_nodes<<<nblk(ndof * nF), TPB, 0, st>>>(h->d_facet_nodes, h->d_bcell_local, h->d_facet_local, d_perm, nF,
+                                                        ndof, n_nodes, d_flag, d_cnt + 1);
+    VH_CUDA(cudaGetLastError());
+    VH_TRY(exclusive_scan(d_flag, d_pos, n_nodes, d_cnt, st));
+    int32_t cnt[2];
+    VH_CUDA(cudaMemcpy(cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost));
+    if (cnt[1] != 0) {
+        dev_free(d_flag); dev_free(d_pos); dev_free(d_cnt); dev_free(d_perm);
+        VH_CHECK(false, VH_ERR_ARG, "vh_set_velocity_layout: node_perm has %d entries outside [0, n_nodes)", cnt[1]);
+    }
+    h->nWn = cnt[0];
+    h->nWn_pad = (h->nWn + 31) / 32 * 32;
+    VH_TRY(dev_alloc(&h->d_wall_slot, h->nWn_pad));
+    k0_wall_slots<<<nblk(n_nodes), TPB, 0, st>>>(d_flag, d_pos, n_nodes, h->node_stride, h->nWn, h->nWn_pad,
+                                                 h->d_wall_slot);
+    k0_rows<<<nblk(ndof * nF), TPB, 0, st>>>(h->d_facet_nodes, h->d_bcell_local, h->d_facet_local, d_perm, d_pos, nF,
+                                             ndof, h->d_row);
     VH_CUDA(cudaGetLastError());
     VH_CUDA(cudaStreamSynchronize(st));
+    dev_free(d_flag); dev_free(d_pos); dev_free(d_cnt);
     dev_free(d_perm);
-    h->launches += 2;
+    h->launches += 5;
     h->order = order;
     h->ndof = ndof;
     h->n_nodes = n_nodes;

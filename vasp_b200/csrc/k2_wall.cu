@@ -1,7 +1,7 @@
 // K2/K3: per-snapshot wall traction + fused time reductions; K4: final index formulas.
 //
 // Replaces the body of the reference's snapshot loop (compute_hemodynamics.py:272-318):
-//   u_p2 = T * u_p1                      (:275)  -> folded into the gather slots built by K0
+//   u_p2 = T * u_p1                      (:275)  -> K1 staged the wall-layer dofs; the row table built by K0 is T
 //   tau = stress()                       (:282)  -> closed-form P2/P1 gradient at the facet vertices, sigma n,
 //                                                   tangential part; SurfaceProjector's solve is the identity for
 //                                                   cells with one exterior facet and a precomputed 3x3-per-contributor
@@ -10,12 +10,14 @@
 //   TWSSG += project_dg(|dtau/dt|)       (:309-312) 7-point degree-5 rule, closed-form P1 mass inverse
 // and the final formulas (:326-346).
 //
-// Thread = one facet x one contiguous chunk of snapshots; tau_prev, the 15 running sums and the facet geometry stay
-// in registers for the whole chunk.  A warp covers 32 consecutive work items (facets) so the table loads and the
-// partial-sum stores are coalesced; the velocity gather goes through the read-only path.  Chunks other than the
-// first recompute tau of the snapshot before them (TWSSG's one-step dependence) instead of communicating.  Partial
-// sums of the blockDim.y chunks of a CTA are added in shared memory in fixed order, written to `part`, and folded
-// into the running sums by k3_fold in fixed order: results are bitwise reproducible for a given launch shape.
+// Work decomposition: one WARP per (facet, time segment); the 32 LANES are 32 consecutive snapshots.  With the
+// time-major block W that K1 wrote, every load of a cell dof is 32 consecutive doubles (256 B): full sectors, two L1
+// wavefronts.  Facet geometry is warp-uniform (broadcast loads), the multi-facet-cell branch is warp-uniform (no
+// divergence), tau of the previous snapshot comes from the neighbouring lane (shuffle) and each lane keeps its
+// share of the 15 running sums in registers until one fixed-order butterfly at the end.  A segment that has a
+// predecessor column computes it in lane 0 of its first pass instead of communicating with the previous segment
+// (TWSSG's one-step dependence).  Partial sums of the segments go to `part` and are folded into the running sums
+// by k3_fold in fixed order: results are bitwise reproducible for a given launch shape.
 //
 // Local vertex labels are facet-canonical (K0): 0,1,2 = the facet's vertices in boundary-cell order, 3 = the
 // opposite vertex; P2 edge dofs 4..9 = e01,e02,e12,e03,e13,e23.
@@ -32,8 +34,8 @@ struct Dofs {
 
 __host__ __device__ constexpr int edge_dof(int a, int b) {
     // canonical edge order e01,e02,e12,e03,e13,e23 -> 4..9
-    return (a > b) ? edge_dof(b, a)
-                   : (b == 1) ? 4 : (b == 2) ? 5 + a : 7 + a;
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    return hi == 1 ? 4 : hi == 2 ? 5 + lo : 7 + lo;
 }
 static_assert(edge_dof(0, 1) == 4 && edge_dof(0, 2) == 5 && edge_dof(1, 2) == 6 && edge_dof(0, 3) == 7 &&
                   edge_dof(1, 3) == 8 && edge_dof(2, 3) == 9 && edge_dof(3, 1) == 8,
@@ -49,14 +51,16 @@ struct Vel {
     double x[10], y[10], z[10];
 };
 
+// velocity of the cell dofs at column `col` of the staged block; base[k] = 3 * row[k] * ld
 template <int ORDER>
-__device__ __forceinline__ void load_vel(const double* __restrict__ u, const int32_t (&slot)[10], int64_t o0,
-                                         int64_t o1, int64_t o2, Vel& v) {
+__device__ __forceinline__ void load_vel(const double* __restrict__ W, const int64_t (&base)[10], int64_t ld,
+                                         int64_t col, Vel& v) {
 #pragma unroll
     for (int k = 0; k < Dofs<ORDER>::N; ++k) {
-        v.x[k] = __ldg(u + o0 + slot[k]);
-        v.y[k] = __ldg(u + o1 + slot[k]);
-        v.z[k] = __ldg(u + o2 + slot[k]);
+        const double* p = W + base[k] + col;
+        v.x[k] = __ldg(p);
+        v.y[k] = __ldg(p + ld);
+        v.z[k] = __ldg(p + 2 * ld);
     }
 }
 
@@ -200,114 +204,123 @@ __device__ __forceinline__ void twssg_project(const double (&w)[9], double (&p)[
     }
 }
 
+__device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+
 struct K2Args {
     FacetTables T;
-    const double* u;        // first non-halo snapshot
-    int64_t stride;         // doubles between snapshots
-    int64_t n_snap;
-    int64_t chunk;          // snapshots per thread
-    int prev_mode;          // 0: zero, 1: tau_last, 2: recompute from snapshot -1
+    const double* W;        // staged block (K1)
+    int64_t ld;
+    int ncol;               // columns in the block
+    int r0;                 // first real column (1 when column 0 is a halo snapshot that only seeds tau_prev)
+    int seg_len;            // real snapshots per segment (blockIdx.y), a multiple of K2_COLS
+    int prev_mode;          // tau_prev of the first real column when r0 == 0: 0 zero, 1 tau_last_in
     const double* tau_last_in;
     double* tau_last_out;   // [9][nF]
     double* part;           // [gridDim.y][15][nF]
-    double* wss_out;        // [n_snap][nF][9] or null
+    double* wss_out;        // [ncol - r0][nF][9] or null
     double mu, inv_dt;
-    int64_t off0, off1, off2;
 };
 
-template <int ORDER>
-__global__ void __launch_bounds__(256) k2_traction(const K2Args a) {
-    extern __shared__ double sm[];  // [blockDim.y][15][blockDim.x]
+constexpr int K2_WARPS = 4;
+constexpr int K2_COLS = 31;  // real columns per lane pass; lane 0 recomputes the column before them
+
+// MULTI = false: facets whose cell owns no other exterior facet (work[0, multi_start)); MULTI = true: the rest.
+template <int ORDER, bool MULTI>
+__global__ void __launch_bounds__(32 * K2_WARPS) k2_wall(const K2Args a) {
     const FacetTables& T = a.T;
     const int64_t nF = T.nF;
-    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t cid = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
-    const int64_t s0 = cid * a.chunk;
-    const int64_t s1 = min(s0 + a.chunk, a.n_snap);
-    const int32_t f = (w < T.n_work) ? T.work[w] : -1;
-    const bool is_multi = w >= T.multi_start;
-    const int64_t m = w - T.multi_start;
+    const int lane = threadIdx.x & 31;
+    const int64_t wi = (int64_t)blockIdx.x * K2_WARPS + (threadIdx.x >> 5);
+    const int64_t w = MULTI ? wi + T.multi_start : wi;
+    if (w >= (MULTI ? T.n_work : T.multi_start)) return;
+    const int32_t f = T.work[w];
+    if (f < 0) return;  // padding entry (warp-uniform)
+    // P1 data in a cell with one exterior facet: tau is the same at the three facet vertices, so one magnitude and
+    // P(|w|) = |w| exactly (the projection reproduces constants)
+    constexpr bool FLAT = (ORDER == 1) && !MULTI;
+    constexpr int NT = FLAT ? 3 : 9;
+
+    int64_t base[10];
+    double g[4][3], n[3], gam[4];
+#pragma unroll
+    for (int k = 0; k < Dofs<ORDER>::N; ++k) base[k] = 3 * (int64_t)T.row[(int64_t)k * nF + f] * a.ld;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) g[b][d] = T.glam[(int64_t)(3 * b + d) * nF + f];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) n[d] = T.normal[(int64_t)d * nF + f];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) gam[b] = g[b][0] * n[0] + g[b][1] * n[1] + g[b][2] * n[2];
+
+    const int seg0 = a.r0 + (int)blockIdx.y * a.seg_len;  // first real column of this segment
+    const int seg1 = min(seg0 + a.seg_len, a.ncol);
 
     double acc[VH_NSUM];
 #pragma unroll
     for (int i = 0; i < VH_NSUM; ++i) acc[i] = 0.0;
 
-    if (f >= 0 && s0 < s1) {
-        int32_t slot[10];
-        double g[4][3], n[3], gam[4];
-#pragma unroll
-        for (int k = 0; k < Dofs<ORDER>::N; ++k) slot[k] = T.slot[(int64_t)k * nF + f];
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-#pragma unroll
-            for (int d = 0; d < 3; ++d) g[b][d] = T.glam[(int64_t)(3 * b + d) * nF + f];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) n[d] = T.normal[(int64_t)d * nF + f];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) gam[b] = g[b][0] * n[0] + g[b][1] * n[1] + g[b][2] * n[2];
-
+    for (int c0 = seg0; c0 < seg1; c0 += K2_COLS) {
+        const int col = c0 + lane - 1;  // lane 0: the column before this pass
+        const bool live = lane > 0 && col < seg1;
         Vel v;
-        double prev[9], tau[9];
-        if (s0 > 0 || a.prev_mode == 2) {
-            load_vel<ORDER>(a.u + (s0 - 1) * a.stride, slot, a.off0, a.off1, a.off2, v);
-            if (is_multi)
-                tau_multi<ORDER>(g, v, a.mu, T.m_lf, T.m_w, m, T.nMulti, prev);
-            else
-                tau_single<ORDER>(g, n, gam, v, a.mu, prev);
-        } else if (a.prev_mode == 1) {
+        load_vel<ORDER>(a.W, base, a.ld, min(max(col, 0), seg1 - 1), v);
+        double tau[9];
+        if (MULTI)
+            tau_multi<ORDER>(g, v, a.mu, T.m_lf, T.m_w, wi, T.nMulti, tau);
+        else
+            tau_single<ORDER>(g, n, gam, v, a.mu, tau);
+        if (col < 0) {  // no column before the block's first: tau_prev is zero or carried over from the last launch
 #pragma unroll
-            for (int i = 0; i < 9; ++i) prev[i] = a.tau_last_in[(int64_t)i * nF + f];
-        } else {
-#pragma unroll
-            for (int i = 0; i < 9; ++i) prev[i] = 0.0;
+            for (int i = 0; i < NT; ++i) tau[i] = a.prev_mode == 1 ? a.tau_last_in[(int64_t)i * nF + f] : 0.0;
         }
-
-        for (int64_t s = s0; s < s1; ++s) {
-            load_vel<ORDER>(a.u + s * a.stride, slot, a.off0, a.off1, a.off2, v);
-            if (is_multi)
-                tau_multi<ORDER>(g, v, a.mu, T.m_lf, T.m_w, m, T.nMulti, tau);
-            else
-                tau_single<ORDER>(g, n, gam, v, a.mu, tau);
+        double dw[9];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) dw[i] = (tau[i] - shfl_up1(tau[i])) * a.inv_dt;
+        if (live) {
+            if (FLAT) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) acc[i] += tau[i];
+                acc[9] += norm3(tau[0], tau[1], tau[2]);
+                acc[12] += norm3(dw[0], dw[1], dw[2]);
+#pragma unroll
+                for (int i = 3; i < 9; ++i) tau[i] = tau[i - 3];
+            } else {
+                double p[3];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) acc[i] += tau[i];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) acc[9 + j] += norm3(tau[3 * j], tau[3 * j + 1], tau[3 * j + 2]);
+                twssg_project(dw, p);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) acc[12 + j] += p[j];
+            }
             if (a.wss_out) {
-                double* o = a.wss_out + (s * nF + f) * 9;
+                double* o = a.wss_out + ((int64_t)(col - a.r0) * nF + f) * 9;
 #pragma unroll
                 for (int i = 0; i < 9; ++i) o[i] = tau[i];
             }
-            double dw[9], p[3];
+            if (col == a.ncol - 1) {
 #pragma unroll
-            for (int i = 0; i < 9; ++i) {
-                acc[i] += tau[i];
-                dw[i] = (tau[i] - prev[i]) * a.inv_dt;
-                prev[i] = tau[i];
+                for (int i = 0; i < 9; ++i) a.tau_last_out[(int64_t)i * nF + f] = tau[i];
             }
-#pragma unroll
-            for (int j = 0; j < 3; ++j) acc[9 + j] += norm3(tau[3 * j], tau[3 * j + 1], tau[3 * j + 2]);
-            twssg_project(dw, p);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) acc[12 + j] += p[j];
-        }
-        if (s1 == a.n_snap) {
-#pragma unroll
-            for (int i = 0; i < 9; ++i) a.tau_last_out[(int64_t)i * nF + f] = prev[i];
         }
     }
 
-    // fixed-order reduction over the CTA's chunk rows, then one coalesced store per sum
-    const int bx = blockDim.x, by = blockDim.y;
-    if (by > 1) {
+    // fixed-order butterfly over the 32 lanes, then lane 0 stores the segment's partial sums
 #pragma unroll
-        for (int i = 0; i < VH_NSUM; ++i) sm[((int64_t)threadIdx.y * VH_NSUM + i) * bx + threadIdx.x] = acc[i];
-        __syncthreads();
-        if (threadIdx.y == 0) {
+    for (int i = 0; i < VH_NSUM; ++i) {
+        if (FLAT && !(i < 3 || i == 9 || i == 12)) continue;
 #pragma unroll
-            for (int i = 0; i < VH_NSUM; ++i) {
-                double t = acc[i];
-                for (int y = 1; y < by; ++y) t += sm[((int64_t)y * VH_NSUM + i) * bx + threadIdx.x];
-                acc[i] = t;
-            }
-        }
+        for (int d = 16; d >= 1; d >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], d);
     }
-    if (threadIdx.y == 0 && f >= 0) {
+    if (FLAT) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) acc[3 + i] = acc[6 + i] = acc[i];
+        acc[10] = acc[11] = acc[9];
+        acc[13] = acc[14] = acc[12];
+    }
+    if (lane == 0) {
         double* p = a.part + (int64_t)blockIdx.y * VH_NSUM * nF + f;
 #pragma unroll
         for (int i = 0; i < VH_NSUM; ++i) p[(int64_t)i * nF] = acc[i];
@@ -350,7 +363,7 @@ __global__ void k4_indices(const double* __restrict__ sums, int64_t nF, double c
 FacetTables vh_tables(const vh_handle* h) {
     FacetTables T;
     T.nF = h->nF;
-    T.slot = h->d_slot;
+    T.row = h->d_row;
     T.glam = h->d_glam;
     T.normal = h->d_normal;
     T.work = h->d_work;
@@ -376,70 +389,116 @@ int k_free_run_buffers(vh_handle* h) {
         h->d_stage[i] = h->d_wss_stage[i] = nullptr;
     }
     h->stage_cap = h->wss_stage_cap = 0;
+    if (h->d_W) cudaFree(h->d_W);
+    h->d_W = nullptr;
+    h->w_ld = 0;
     h->begun = false;
+    return VH_OK;
+}
+
+// Columns per staged block: as many as fit ~1/8 of the free memory (at most 4 GiB), between 64 and 4096; a
+// batch_snapshots tuning value caps it (one column more than the batch, for the halo)
+static int ensure_stage_block(vh_handle* h, int64_t want_cols) {
+    int64_t cap = h->w_ld;
+    if (h->batch_snapshots > 0 && want_cols > h->batch_snapshots + 1) want_cols = h->batch_snapshots + 1;
+    if (cap >= want_cols || cap >= 4096) return VH_OK;
+    size_t free_b = 0, total_b = 0;
+    VH_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (h->d_W) free_b += (size_t)(h->nWn_pad * 24 * h->w_ld);
+    int64_t budget = (int64_t)(free_b / 8);
+    if (budget > (4LL << 30)) budget = 4LL << 30;
+    int64_t cols = budget / (h->nWn_pad * 24);
+    if (cols > 4096) cols = 4096;
+    if (cols > want_cols) cols = want_cols;
+    if (cols < 64 && h->batch_snapshots <= 0) cols = 64;
+    cols = (cols + 31) / 32 * 32;
+    if (cols <= cap) return VH_OK;
+    if (h->d_W) cudaFree(h->d_W);
+    h->d_W = nullptr;
+    h->w_ld = 0;
+    VH_CUDA(cudaMalloc(&h->d_W, (size_t)(h->nWn_pad * 24 * cols)));
+    h->w_ld = cols;
     return VH_OK;
 }
 
 int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_elems, int prev_mode, double* d_wss) {
     if (n_snap <= 0) return VH_OK;
     const int64_t nF = h->nF;
-    // launch shape: x = 64 work items, y = up to 4 chunk rows; chunk length so that the grid is a few waves of
-    // 148 SMs x resident CTAs, but never shorter than 4 snapshots (halo recompute <= 25 %)
-    const int bx = 64;
-    const int64_t gx = (h->n_work + bx - 1) / bx;
-    int64_t chunk = h->chunk_snapshots;
-    if (chunk <= 0) {
-        const int64_t target_threads = (int64_t)h->sm_count * 512 * 2;
-        int64_t want_chunks = (target_threads + gx * bx - 1) / (gx * bx);
-        if (want_chunks < 1) want_chunks = 1;
-        chunk = (n_snap + want_chunks - 1) / want_chunks;
-        if (chunk < 4) chunk = 4;
+    VH_TRY(ensure_stage_block(h, n_snap + 1));
+    const int64_t n_single = h->multi_start, n_multi = h->n_work - h->multi_start;
+    const unsigned gx_single = (unsigned)((n_single + K2_WARPS - 1) / K2_WARPS);
+    const unsigned gx_multi = (unsigned)((n_multi + K2_WARPS - 1) / K2_WARPS);
+    int64_t pos = 0;
+    while (pos < n_snap) {
+        const int halo = (pos == 0 && prev_mode == 2) ? 1 : 0;
+        int64_t nb = n_snap - pos;
+        if (nb + halo > h->w_ld) nb = h->w_ld - halo;
+        const int64_t ncol = nb + halo;
+        // segment length = p lane passes of 31 real snapshots: the fewest segments that still give every SM ~64
+        // (facet, segment) warps to schedule
+        int64_t p = (h->chunk_snapshots + K2_COLS - 1) / K2_COLS;
+        if (p <= 0) {
+            const int64_t target_warps = (int64_t)h->sm_count * 64;
+            for (p = (nb + K2_COLS - 1) / K2_COLS; p > 1; --p)
+                if (h->n_work * ((nb + K2_COLS * p - 1) / (K2_COLS * p)) >= target_warps) break;
+        }
+        const int64_t seg = K2_COLS * p;
+        const int64_t gy = (nb + seg - 1) / seg;
+        VH_CHECK(gy <= 65535, VH_ERR_ARG, "k2_launch: too many segments (%lld); raise chunk_snapshots", (long long)gy);
+        if (gy > h->part_cap) {
+            if (h->d_part) cudaFree(h->d_part);
+            h->d_part = nullptr;
+            h->part_cap = 0;
+            VH_CUDA(cudaMalloc(&h->d_part, sizeof(double) * VH_NSUM * nF * gy));
+            h->part_cap = gy;
+        }
+        const bool prof = h->profile && h->prof_used + 3 <= h->prof_pool.size();
+        if (prof) cudaEventRecord(h->prof_pool[h->prof_used], h->s_compute);
+        VH_TRY(k1_launch(h, d_u + (pos - halo) * stride_elems, ncol, stride_elems));
+        if (prof) cudaEventRecord(h->prof_pool[h->prof_used + 1], h->s_compute);
+        K2Args a;
+        a.T = vh_tables(h);
+        a.W = h->d_W;
+        a.ld = h->w_ld;
+        a.ncol = (int)ncol;
+        a.r0 = halo;
+        a.seg_len = (int)seg;
+        a.prev_mode = pos == 0 ? prev_mode : 1;
+        a.tau_last_in = h->d_tau_last[h->tau_cur];
+        a.tau_last_out = h->d_tau_last[h->tau_cur ^ 1];
+        h->tau_cur ^= 1;
+        a.part = h->d_part;
+        a.wss_out = d_wss ? d_wss + pos * nF * 9 : nullptr;
+        a.mu = h->mu;
+        a.inv_dt = 1.0 / h->dt;
+        dim3 block(32 * K2_WARPS);
+        if (gx_single) {
+            dim3 grid(gx_single, (unsigned)gy);
+            if (h->order == 2)
+                k2_wall<2, false><<<grid, block, 0, h->s_compute>>>(a);
+            else
+                k2_wall<1, false><<<grid, block, 0, h->s_compute>>>(a);
+            h->launches += 1;
+        }
+        if (gx_multi) {
+            dim3 grid(gx_multi, (unsigned)gy);
+            if (h->order == 2)
+                k2_wall<2, true><<<grid, block, 0, h->s_compute>>>(a);
+            else
+                k2_wall<1, true><<<grid, block, 0, h->s_compute>>>(a);
+            h->launches += 1;
+        }
+        if (prof) {
+            cudaEventRecord(h->prof_pool[h->prof_used + 2], h->s_compute);
+            h->prof_used += 3;
+        }
+        VH_CUDA(cudaGetLastError());
+        const int64_t n = VH_NSUM * nF;
+        k3_fold<<<(unsigned)((n + 255) / 256), 256, 0, h->s_compute>>>(h->d_sums, h->d_part, n, gy);
+        VH_CUDA(cudaGetLastError());
+        h->launches += 1;
+        pos += nb;
     }
-    if (chunk > n_snap) chunk = n_snap;
-    const int64_t n_chunks = (n_snap + chunk - 1) / chunk;
-    int by = n_chunks >= 4 ? 4 : (n_chunks >= 2 ? 2 : 1);
-    const int64_t gy = (n_chunks + by - 1) / by;
-    VH_CHECK(gy <= 65535, VH_ERR_ARG, "k2_launch: too many chunk groups (%lld); raise chunk_snapshots", (long long)gy);
-    if (gy > h->part_cap) {
-        if (h->d_part) cudaFree(h->d_part);
-        h->d_part = nullptr;
-        VH_CUDA(cudaMalloc(&h->d_part, sizeof(double) * VH_NSUM * nF * gy));
-        h->part_cap = gy;
-    }
-    K2Args a;
-    a.T = vh_tables(h);
-    a.u = d_u;
-    a.stride = stride_elems;
-    a.n_snap = n_snap;
-    a.chunk = chunk;
-    a.prev_mode = prev_mode;
-    a.tau_last_in = h->d_tau_last[h->tau_cur];
-    a.tau_last_out = h->d_tau_last[h->tau_cur ^ 1];
-    h->tau_cur ^= 1;
-    a.part = h->d_part;
-    a.wss_out = d_wss;
-    a.mu = h->mu;
-    a.inv_dt = 1.0 / h->dt;
-    a.off0 = h->comp_offset[0];
-    a.off1 = h->comp_offset[1];
-    a.off2 = h->comp_offset[2];
-    dim3 grid((unsigned)gx, (unsigned)gy), block(bx, by);
-    size_t smem = by > 1 ? sizeof(double) * VH_NSUM * bx * by : 0;
-    const bool prof = h->profile && h->prof_used + 2 <= h->prof_pool.size();
-    if (prof) cudaEventRecord(h->prof_pool[h->prof_used], h->s_compute);
-    if (h->order == 2)
-        k2_traction<2><<<grid, block, smem, h->s_compute>>>(a);
-    else
-        k2_traction<1><<<grid, block, smem, h->s_compute>>>(a);
-    if (prof) {
-        cudaEventRecord(h->prof_pool[h->prof_used + 1], h->s_compute);
-        h->prof_used += 2;
-    }
-    VH_CUDA(cudaGetLastError());
-    const int64_t n = VH_NSUM * nF;
-    k3_fold<<<(unsigned)((n + 255) / 256), 256, 0, h->s_compute>>>(h->d_sums, h->d_part, n, gy);
-    VH_CUDA(cudaGetLastError());
-    h->launches += 2;
     h->count += n_snap;
     h->have_tau_last = true;
     return VH_OK;

@@ -104,9 +104,10 @@ class HemoEngine:
         self._refresh_sizes()
 
     def _refresh_sizes(self) -> None:
-        n = (C.c_int64 * 6)()
+        n = (C.c_int64 * 7)()
         check(self._lib.vh_get_sizes(self._h, n))
-        self.nF, self.nBV, self.n_wall_cells, self.n_multi, self.ndof, self.n_nodes = (int(x) for x in n)
+        (self.nF, self.nBV, self.n_wall_cells, self.n_multi, self.ndof, self.n_nodes,
+         self.n_wall_nodes) = (int(x) for x in n)
 
     def maps(self) -> Dict[str, np.ndarray]:
         nF = self.nF
@@ -199,11 +200,11 @@ class HemoEngine:
     def set_profile(self, on: bool) -> None:
         check(self._lib.vh_set_profile(self._h, int(bool(on))))
 
-    def kernel_profile(self) -> Tuple[float, int]:
-        """(summed k2_traction milliseconds, launches) since the last call."""
-        ms, n = C.c_double(), C.c_int64()
-        check(self._lib.vh_get_kernel_profile(self._h, C.byref(ms), C.byref(n)))
-        return ms.value, int(n.value)
+    def kernel_profile(self) -> Tuple[float, float, int]:
+        """(summed k1_stage ms, summed k2_wall ms, launches of each) since the last call."""
+        m1, m2, n = C.c_double(), C.c_double(), C.c_int64()
+        check(self._lib.vh_get_kernel_profile(self._h, C.byref(m1), C.byref(m2), C.byref(n)))
+        return m1.value, m2.value, int(n.value)
 
     def finalize_async(self, n_total: int) -> None:
         """Enqueue the final formulas only; results stay on the device (bench: device-resident timing)."""
