@@ -61,7 +61,7 @@ int nccl_load() {
 int ensure_run_buffers(vh_handle* h) {
     const int64_t nF = h->nF;
     if (!h->d_sums) {
-        VH_CUDA(cudaMalloc(&h->d_sums, sizeof(double) * VH_NSUM * nF));
+        VH_CUDA(cudaMalloc(&h->d_sums, sizeof(double) * (VH_NSUM * nF + 1)));  // + the snapshot count (all-reduce)
         VH_CUDA(cudaMalloc(&h->d_tau_last[0], sizeof(double) * 9 * nF));
         VH_CUDA(cudaMalloc(&h->d_tau_last[1], sizeof(double) * 9 * nF));
         VH_CUDA(cudaMalloc(&h->d_out5, sizeof(double) * 15 * nF));
@@ -77,6 +77,8 @@ int check_ready(vh_handle* h, const char* who) {
     VH_CHECK(h->begun, VH_ERR_ARG, "%s: call vh_begin first", who);
     return VH_OK;
 }
+
+__global__ void k_set_scalar(double* p, double v) { *p = v; }
 
 __global__ void k_flush(double* __restrict__ p, int64_t n, double v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,6 +111,9 @@ int vh_create(int device, vh_handle** out) {
     h->sm_count = prop.multiProcessorCount;
     VH_CUDA(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
     VH_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    VH_CUDA(cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking));
+    VH_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    VH_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         VH_CUDA(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
         VH_CUDA(cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming));
@@ -130,7 +135,7 @@ int vh_destroy(vh_handle* h) {
     k_free_run_buffers(h);
     void* ptrs[] = {h->d_xyz, h->d_tets, h->d_facet_cell, h->d_facet_verts, h->d_bcell_parent, h->d_btopology,
                     h->d_bvert_parent, h->d_facet_local, h->d_bcell_local, h->d_blocal_soa, h->d_glam, h->d_normal,
-                    h->d_area, h->d_work, h->d_m_lf, h->d_m_w, h->d_facet_nodes, h->d_row, h->d_wall_slot, h->d_flush, h->d_scalar};
+                    h->d_area, h->d_work, h->d_m_lf, h->d_m_w, h->d_m_mat, h->d_facet_nodes, h->d_row, h->d_wall_slot, h->d_flush, h->d_scalar};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 2; ++i) {
@@ -143,8 +148,11 @@ int vh_destroy(vh_handle* h) {
     cudaEventDestroy(h->ev_k0);
     cudaEventDestroy(h->ev_k1);
     for (auto& e : h->prof_pool) cudaEventDestroy(e);
+    cudaEventDestroy(h->ev_fork);
+    cudaEventDestroy(h->ev_join);
     cudaStreamDestroy(h->s_compute);
     cudaStreamDestroy(h->s_copy);
+    cudaStreamDestroy(h->s_aux);
     delete h;
     return VH_OK;
 }
@@ -231,9 +239,10 @@ int vh_begin(vh_handle* h, double mu, double dt) {
     h->mu = mu;
     h->dt = dt;
     h->count = 0;
+    h->count_on_device = false;
     h->have_tau_last = false;
     h->kernel_ms = h->h2d_ms = 0.0;
-    VH_CUDA(cudaMemsetAsync(h->d_sums, 0, sizeof(double) * VH_NSUM * h->nF, h->s_compute));
+    VH_CUDA(cudaMemsetAsync(h->d_sums, 0, sizeof(double) * (VH_NSUM * h->nF + 1), h->s_compute));
     VH_CUDA(cudaMemsetAsync(h->d_tau_last[0], 0, sizeof(double) * 9 * h->nF, h->s_compute));
     VH_CUDA(cudaMemsetAsync(h->d_tau_last[1], 0, sizeof(double) * 9 * h->nF, h->s_compute));
     h->begun = true;  // stream-ordered: no host sync needed before the first push
@@ -406,6 +415,12 @@ int vh_get_sums(vh_handle* h, double* sums, int64_t* count) {
     VH_TRY(check_ready(h, "vh_get_sums"));
     VH_CUDA(cudaStreamSynchronize(h->s_compute));
     if (sums) VH_CUDA(cudaMemcpy(sums, h->d_sums, sizeof(double) * VH_NSUM * h->nF, cudaMemcpyDeviceToHost));
+    if (h->count_on_device) {  // left there by vh_nccl_allreduce_sums, which does not synchronise
+        double cnt = 0.0;
+        VH_CUDA(cudaMemcpy(&cnt, h->d_sums + VH_NSUM * h->nF, sizeof(double), cudaMemcpyDeviceToHost));
+        h->count = (int64_t)(cnt + 0.5);
+        h->count_on_device = false;
+    }
     if (count) *count = h->count;
     return VH_OK;
 }
@@ -416,6 +431,7 @@ int vh_set_sums(vh_handle* h, const double* sums, int64_t count) {
     VH_CUDA(cudaStreamSynchronize(h->s_compute));
     VH_CUDA(cudaMemcpy(h->d_sums, sums, sizeof(double) * VH_NSUM * h->nF, cudaMemcpyHostToDevice));
     h->count = count;
+    h->count_on_device = false;
     return VH_OK;
 }
 
@@ -614,14 +630,16 @@ int vh_nccl_init(vh_handle* h, const char id[128], int rank, int world) {
 int vh_nccl_allreduce_sums(vh_handle* h) {
     VH_TRY(check_ready(h, "vh_nccl_allreduce_sums"));
     VH_CHECK(h->nccl_comm, VH_ERR_NCCL, "vh_nccl_allreduce_sums: call vh_nccl_init first");
-    double cnt = (double)h->count;
-    VH_CUDA(cudaMemcpyAsync(h->d_scalar, &cnt, sizeof(double), cudaMemcpyHostToDevice, h->s_compute));
-    VH_NCCL(g_nccl.AllReduce(h->d_sums, h->d_sums, (size_t)(VH_NSUM * h->nF), ncclDouble, ncclSum,
-                             (ncclComm_t)h->nccl_comm, h->s_compute));
-    VH_NCCL(g_nccl.AllReduce(h->d_scalar, h->d_scalar, 1, ncclDouble, ncclSum, (ncclComm_t)h->nccl_comm, h->s_compute));
-    VH_CUDA(cudaMemcpyAsync(&cnt, h->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, h->s_compute));
-    VH_CUDA(cudaStreamSynchronize(h->s_compute));
-    h->count = (int64_t)(cnt + 0.5);
+    // one collective, stream-ordered, no host synchronisation: the snapshot count rides behind the 15 * nF sums
+    const int64_t n = VH_NSUM * h->nF;
+    if (!h->count_on_device) {
+        k_set_scalar<<<1, 1, 0, h->s_compute>>>(h->d_sums + n, (double)h->count);
+        VH_CUDA(cudaGetLastError());
+    }
+    VH_NCCL(g_nccl.AllReduce(h->d_sums, h->d_sums, (size_t)(n + 1), ncclDouble, ncclSum, (ncclComm_t)h->nccl_comm,
+                             h->s_compute));
+    h->count_on_device = true;
+    h->launches += 1;
     return VH_OK;
 }
 

@@ -37,6 +37,7 @@ void vh_set_error(const char* fmt, ...);
 // Number of running sums per facet: 9 (sum tau) + 3 (sum |tau|) + 3 (sum P(|dtau/dt|)); SoA rows of length nF.
 constexpr int VH_NSUM = 15;
 constexpr int VH_MAX_CONTRIB = 4;  // a tet has at most 4 exterior facets
+constexpr int VH_MROW = 10;        // row length of the multi-facet operator: 9 outputs padded for 16-byte loads
 
 // Per-facet constants in HBM, all SoA over facets (row r of an array with R rows: ptr[r * nF + f]).
 struct FacetTables {
@@ -48,16 +49,17 @@ struct FacetTables {
     // facets, starting at multi_start; -1 entries are padding
     const int32_t* work;
     int64_t n_work, multi_start;
-    // multi-facet cells (SurfaceProjector's 4x4 blocks): per multi facet m = work index - multi_start
-    const int8_t* m_lf;      // [4][nMulti] canonical label a of contributor face (opposite vertex a), -1: none
-    const double* m_w;       // [4*9][nMulti] W[a][j][kk]
+    // multi-facet cells (SurfaceProjector's 4x4 blocks): per multi facet m = work index - multi_start the dense
+    // operator tau[3 j + ci] = -mu * sum_q m_mat[m][q][3 j + ci] * u[q],  q = 3 * (cell dof) + component
+    const double* m_mat;     // [nMulti][3 * ndof][VH_MROW]
     int64_t nMulti;
 };
 
 struct vh_handle {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_aux = nullptr;  // s_aux: multi-facet-cell K2 launch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     // mesh
     int64_t nv = 0, nc = 0;
@@ -71,8 +73,9 @@ struct vh_handle {
     double *d_glam = nullptr, *d_normal = nullptr, *d_area = nullptr;  // SoA
     int32_t* d_work = nullptr;
     int64_t n_work = 0, multi_start = 0;
-    int8_t* d_m_lf = nullptr;
-    double* d_m_w = nullptr;
+    int8_t* d_m_lf = nullptr;     // [4][nMulti] canonical label a of contributor face (opposite vertex a), -1: none
+    double* d_m_w = nullptr;      // [4*9][nMulti] W[a][j][kk] of SurfaceProjector's block solve
+    double* d_m_mat = nullptr;    // [nMulti][3 * ndof][VH_MROW], built with the velocity layout (needs the order)
 
     // velocity layout
     int order = 0, ndof = 0;
@@ -91,8 +94,9 @@ struct vh_handle {
     double mu = 0.0, dt = 0.0;
     bool begun = false;
     int64_t count = 0;         // snapshots accumulated
+    bool count_on_device = false;  // after an all-reduce the global count sits behind the sums until someone asks
     bool have_tau_last = false;
-    double* d_sums = nullptr;      // [15][nF]
+    double* d_sums = nullptr;      // [15][nF] + 1 (snapshot count, filled for the all-reduce)
     double* d_tau_last[2] = {nullptr, nullptr};  // [9][nF], ping-pong (read by first chunk, written by last)
     int tau_cur = 0;
     double* d_out5 = nullptr;      // [5][3*nF] TAWSS, OSI, RRT, ECAP, TWSSG

@@ -401,6 +401,75 @@ __global__ void k0_multi_weights(const int32_t* __restrict__ work, int64_t multi
     }
 }
 
+// Dense operator of a multi-facet-cell facet (thread = (multi facet m, cell dof k), canonical labels):
+//   tau_f(j) = sum_a sum_kk W[a][j][kk] Ft_a(v_kk),   Ft_a(V) = -mu (I - n_a n_a^T) (G(V) + G(V)^T) n_a,
+//   G(V) = sum_k u_k (x) d_k(V),  d_k(V) = grad phi_k at vertex V:
+//     P1: g_k;  P2 vertex dof b: 3 g_V if b == V else -g_b;  P2 edge dof (p,q): 4 g_q if p == V, 4 g_p if q == V, else 0
+//   => (G + G^T) n = sum_k [(d_k . n) I + d_k n^T] u_k.
+// m_mat[m][3 k + c][3 j + ci] collects the coefficient of u_k[c] in tau_f(j)[ci] without the factor -mu.
+__global__ void k0_multi_matrix(int64_t nMulti, int ndof, const int32_t* __restrict__ work, int64_t multi_start,
+                                int64_t nF, const double* __restrict__ glam, const int8_t* __restrict__ m_lf,
+                                const double* __restrict__ m_w, double* __restrict__ m_mat) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nMulti * ndof) return;
+    const int64_t m = idx / ndof;
+    const int k = (int)(idx % ndof);
+    const int32_t f = work[multi_start + m];
+    double g[4][3];
+    for (int b = 0; b < 4; ++b)
+        for (int d = 0; d < 3; ++d) g[b][d] = glam[(int64_t)(3 * b + d) * nF + f];
+    double M[3][9];  // [c][3 j + ci]
+    for (int c = 0; c < 3; ++c)
+        for (int i = 0; i < 9; ++i) M[c][i] = 0.0;
+    const int ea[6] = {0, 0, 1, 0, 1, 2}, eb[6] = {1, 2, 2, 3, 3, 3};  // canonical edge dofs 4..9
+    for (int a = 0; a < 4; ++a) {
+        if (m_lf[(int64_t)a * nMulti + m] < 0) continue;
+        double inv = -1.0 / sqrt(g[a][0] * g[a][0] + g[a][1] * g[a][1] + g[a][2] * g[a][2]);
+        double n[3] = {g[a][0] * inv, g[a][1] * inv, g[a][2] * inv};
+        const int vc[3] = {a == 0 ? 1 : 0, a <= 1 ? 2 : 1, a <= 2 ? 3 : 2};
+        for (int kk = 0; kk < 3; ++kk) {
+            const int V = vc[kk];
+            double d[3] = {0.0, 0.0, 0.0};
+            if (ndof == 4) {
+                for (int t = 0; t < 3; ++t) d[t] = g[k][t];
+            } else if (k < 4) {
+                for (int t = 0; t < 3; ++t) d[t] = (k == V) ? 3.0 * g[V][t] : -g[k][t];
+            } else {
+                const int p = ea[k - 4], q = eb[k - 4];
+                if (p == V)
+                    for (int t = 0; t < 3; ++t) d[t] = 4.0 * g[q][t];
+                else if (q == V)
+                    for (int t = 0; t < 3; ++t) d[t] = 4.0 * g[p][t];
+                else
+                    continue;
+            }
+            const double dn = d[0] * n[0] + d[1] * n[1] + d[2] * n[2];
+            // B = (I - n n^T) [(d.n) I + d n^T]
+            double B[3][3];
+            for (int ci = 0; ci < 3; ++ci)
+                for (int c = 0; c < 3; ++c) {
+                    double acc = 0.0;
+                    for (int t = 0; t < 3; ++t) {
+                        const double P = (ci == t ? 1.0 : 0.0) - n[ci] * n[t];
+                        const double A = (t == c ? dn : 0.0) + d[t] * n[c];
+                        acc += P * A;
+                    }
+                    B[ci][c] = acc;
+                }
+            for (int j = 0; j < 3; ++j) {
+                const double wj = m_w[(int64_t)(9 * a + 3 * j + kk) * nMulti + m];
+                for (int ci = 0; ci < 3; ++ci)
+                    for (int c = 0; c < 3; ++c) M[c][3 * j + ci] += wj * B[ci][c];
+            }
+        }
+    }
+    for (int c = 0; c < 3; ++c) {
+        double* out = m_mat + ((m * ndof + k) * 3 + c) * VH_MROW;
+        for (int i = 0; i < 9; ++i) out[i] = M[c][i];
+        out[9] = 0.0;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // P2 node map: uniform grid of the refined-mesh vertices, chained per grid cell
 // ---------------------------------------------------------------------------------------------------------------
@@ -555,7 +624,7 @@ int k0_build_mesh(vh_handle* h, const double* xyz, int64_t nv, const int64_t* te
     dev_free(h->d_xyz); dev_free(h->d_tets); dev_free(h->d_facet_cell); dev_free(h->d_facet_verts);
     dev_free(h->d_bcell_parent); dev_free(h->d_btopology); dev_free(h->d_bvert_parent); dev_free(h->d_facet_local);
     dev_free(h->d_bcell_local); dev_free(h->d_blocal_soa); dev_free(h->d_glam); dev_free(h->d_normal);
-    dev_free(h->d_area); dev_free(h->d_work); dev_free(h->d_m_lf); dev_free(h->d_m_w);
+    dev_free(h->d_area); dev_free(h->d_work); dev_free(h->d_m_lf); dev_free(h->d_m_w); dev_free(h->d_m_mat);
     dev_free(h->d_facet_nodes); dev_free(h->d_row); dev_free(h->d_wall_slot);
     k_free_run_buffers(h);
     h->order = 0;
@@ -753,6 +822,13 @@ int k0_build_velocity_map(vh_handle* h, int order, const double* refined_xyz, in
                                                  h->d_wall_slot);
     k0_rows<<<nblk(ndof * nF), TPB, 0, st>>>(h->d_facet_nodes, h->d_bcell_local, h->d_facet_local, d_perm, d_pos, nF,
                                              ndof, h->d_row);
+    dev_free(h->d_m_mat);
+    VH_TRY(dev_alloc(&h->d_m_mat, h->nMulti * 3 * ndof * VH_MROW));
+    if (h->nMulti > 0) {
+        k0_multi_matrix<<<nblk(h->nMulti * ndof, 64), 64, 0, st>>>(h->nMulti, ndof, h->d_work, h->multi_start, nF, h->d_glam,
+                                                                   h->d_m_lf, h->d_m_w, h->d_m_mat);
+        h->launches += 1;
+    }
     VH_CUDA(cudaGetLastError());
     VH_CUDA(cudaStreamSynchronize(st));
     dev_free(d_flag); dev_free(d_pos); dev_free(d_cnt);

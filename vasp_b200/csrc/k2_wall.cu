@@ -4,20 +4,25 @@
 //   u_p2 = T * u_p1                      (:275)  -> K1 staged the wall-layer dofs; the row table built by K0 is T
 //   tau = stress()                       (:282)  -> closed-form P2/P1 gradient at the facet vertices, sigma n,
 //                                                   tangential part; SurfaceProjector's solve is the identity for
-//                                                   cells with one exterior facet and a precomputed 3x3-per-contributor
-//                                                   weight for cells with several (K0)
+//                                                   cells with one exterior facet and a precomputed dense operator
+//                                                   (K0: block solve folded with the contributing faces) otherwise
 //   TAWSS += |tau|, WSS_mean += tau      (:289-306)
 //   TWSSG += project_dg(|dtau/dt|)       (:309-312) 7-point degree-5 rule, closed-form P1 mass inverse
 // and the final formulas (:326-346).
 //
 // Work decomposition: one WARP per (facet, time segment); the 32 LANES are 32 consecutive snapshots.  With the
 // time-major block W that K1 wrote, every load of a cell dof is 32 consecutive doubles (256 B): full sectors, two L1
-// wavefronts.  Facet geometry is warp-uniform (broadcast loads), the multi-facet-cell branch is warp-uniform (no
-// divergence), tau of the previous snapshot comes from the neighbouring lane (shuffle) and each lane keeps its
-// share of the 15 running sums in registers until one fixed-order butterfly at the end.  A segment that has a
-// predecessor column computes it in lane 0 of its first pass instead of communicating with the previous segment
-// (TWSSG's one-step dependence).  Partial sums of the segments go to `part` and are folded into the running sums
-// by k3_fold in fixed order: results are bitwise reproducible for a given launch shape.
+// wavefronts.  Facet geometry is warp-uniform (broadcast loads), facets of multi-facet cells get their own launch
+// (no divergence), tau of the previous snapshot comes from the neighbouring lane (shuffle) and each lane keeps its
+// share of the 15 running sums in registers until one fixed-order butterfly at the end.  Lane 0 of every lane pass
+// recomputes the column before the pass instead of communicating with the previous pass or segment (TWSSG's
+// one-step dependence), so a pass advances 31 snapshots.  The rows of the next pass are in flight while the
+// current one is computed: cp.async into a per-warp shared-memory ring for P2 (30 rows; every lane copies and later
+// reads only its own column, so no barrier), a register double buffer for P1 (12 rows).  Partial sums of the
+// segments go to `part` and are folded into the running sums by k3_fold in fixed order: results are bitwise
+// reproducible for a given launch shape.  (A TMA variant -- one cp.async.bulk of 288 B per row and pass, mbarrier
+// completion -- was measured 10-20 % slower than cp.async.ca: the copies bypass L1, where neighbouring facets share
+// rows, and are too small to amortise; see DESIGN.md.)
 //
 // Local vertex labels are facet-canonical (K0): 0,1,2 = the facet's vertices in boundary-cell order, 3 = the
 // opposite vertex; P2 edge dofs 4..9 = e01,e02,e12,e03,e13,e23.
@@ -50,19 +55,6 @@ struct Vel {
     // velocity of the cell dofs, one snapshot
     double x[10], y[10], z[10];
 };
-
-// velocity of the cell dofs at column `col` of the staged block; base[k] = 3 * row[k] * ld
-template <int ORDER>
-__device__ __forceinline__ void load_vel(const double* __restrict__ W, const int64_t (&base)[10], int64_t ld,
-                                         int64_t col, Vel& v) {
-#pragma unroll
-    for (int k = 0; k < Dofs<ORDER>::N; ++k) {
-        const double* p = W + base[k] + col;
-        v.x[k] = __ldg(p);
-        v.y[k] = __ldg(p + ld);
-        v.z[k] = __ldg(p + 2 * ld);
-    }
-}
 
 // Tangential traction Ft = F - (F.n) n, F = -mu (grad u + grad u^T) n, at local vertices listed in VS..., for the
 // face with unit normal n.  g[a] = grad lambda_a.
@@ -136,50 +128,6 @@ __device__ __forceinline__ void tau_single(const double (&g)[4][3], const double
     }
 }
 
-template <int ORDER, int A, int V, int KK>
-__device__ __forceinline__ void multi_vertex(const double (&g)[4][3], const double (&n)[3], const double (&gam)[4],
-                                             const Vel& v, const double (&un)[10], const double (&c)[3], double mu,
-                                             const double* __restrict__ w, int64_t wstride, double (&tau)[9]) {
-    double ft[3];
-    ft_vertex<ORDER, V>(g, n, gam, v, un, c, mu, ft);
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        double wj = w[(int64_t)(9 * A + 3 * j + KK) * wstride];
-        tau[3 * j + 0] = fma(wj, ft[0], tau[3 * j + 0]);
-        tau[3 * j + 1] = fma(wj, ft[1], tau[3 * j + 1]);
-        tau[3 * j + 2] = fma(wj, ft[2], tau[3 * j + 2]);
-    }
-}
-
-// contributor = face opposite canonical local vertex A; its vertices are the other three in ascending label order
-template <int ORDER, int A>
-__device__ __forceinline__ void multi_face(const double (&g)[4][3], const Vel& v, double mu,
-                                           const double* __restrict__ w, int64_t wstride, double (&tau)[9]) {
-    double n[3], gam[4], un[10], c[3];
-    double inv = -1.0 / sqrt(g[A][0] * g[A][0] + g[A][1] * g[A][1] + g[A][2] * g[A][2]);
-    n[0] = g[A][0] * inv; n[1] = g[A][1] * inv; n[2] = g[A][2] * inv;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) gam[b] = g[b][0] * n[0] + g[b][1] * n[1] + g[b][2] * n[2];
-    face_common<ORDER>(g, n, gam, v, un, c);
-    constexpr int V0 = A == 0 ? 1 : 0, V1 = A <= 1 ? 2 : 1, V2 = A <= 2 ? 3 : 2;
-    multi_vertex<ORDER, A, V0, 0>(g, n, gam, v, un, c, mu, w, wstride, tau);
-    multi_vertex<ORDER, A, V1, 1>(g, n, gam, v, un, c, mu, w, wstride, tau);
-    multi_vertex<ORDER, A, V2, 2>(g, n, gam, v, un, c, mu, w, wstride, tau);
-}
-
-template <int ORDER>
-__device__ __noinline__ void tau_multi(const double (&g)[4][3], const Vel& v, double mu,
-                                       const int8_t* __restrict__ m_lf, const double* __restrict__ m_w, int64_t m,
-                                       int64_t nMulti, double (&tau)[9]) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) tau[i] = 0.0;
-    const double* w = m_w + m;
-    if (m_lf[0 * nMulti + m] >= 0) multi_face<ORDER, 0>(g, v, mu, w, nMulti, tau);
-    if (m_lf[1 * nMulti + m] >= 0) multi_face<ORDER, 1>(g, v, mu, w, nMulti, tau);
-    if (m_lf[2 * nMulti + m] >= 0) multi_face<ORDER, 2>(g, v, mu, w, nMulti, tau);
-    multi_face<ORDER, 3>(g, v, mu, w, nMulti, tau);
-}
-
 __device__ __forceinline__ double norm3(double a, double b, double c) { return sqrt(fma(a, a, fma(b, b, c * c))); }
 
 // P(|w|) on the boundary triangle: p_j = 12 s_j - 3 sum_i s_i,  s_i = sum_q wq phi_i(x_q) |w(x_q)|   (area cancels)
@@ -212,11 +160,11 @@ struct K2Args {
     int64_t ld;
     int ncol;               // columns in the block
     int r0;                 // first real column (1 when column 0 is a halo snapshot that only seeds tau_prev)
-    int seg_len;            // real snapshots per segment (blockIdx.y), a multiple of K2_COLS
+    int pass_base, pass_extra;  // segment y owns pass_base (+1 if y < pass_extra) lane passes of K2_COLS columns
     int prev_mode;          // tau_prev of the first real column when r0 == 0: 0 zero, 1 tau_last_in
     const double* tau_last_in;
     double* tau_last_out;   // [9][nF]
-    double* part;           // [gridDim.y][15][nF]
+    double* part;           // [gridDim.y][15][n_work]
     double* wss_out;        // [ncol - r0][nF][9] or null
     double mu, inv_dt;
 };
@@ -224,13 +172,55 @@ struct K2Args {
 constexpr int K2_WARPS = 4;
 constexpr int K2_COLS = 31;  // real columns per lane pass; lane 0 recomputes the column before them
 
+__device__ __forceinline__ void cp_async8(uint32_t dst_smem, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Shared-memory ring of the cp.async path: [warp][stage][3 * dof + c][lane]
+template <int ORDER>
+constexpr int k2_smem_bytes() {
+    return ORDER == 2 ? K2_WARPS * 2 * 3 * Dofs<ORDER>::N * 32 * (int)sizeof(double) : 0;
+}
+
+// tau of a facet whose cell owns several exterior facets: dense operator from K0, warp-uniform coefficient loads
+template <int ORDER>
+__device__ __forceinline__ void tau_dense(const double* __restrict__ M, const Vel& v, double mu, double (&tau)[9]) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) tau[i] = 0.0;
+#pragma unroll
+    for (int k = 0; k < Dofs<ORDER>::N; ++k) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double val = c == 0 ? v.x[k] : c == 1 ? v.y[k] : v.z[k];
+            const double2* row = reinterpret_cast<const double2*>(M + (3 * k + c) * VH_MROW);
+#pragma unroll
+            for (int h2 = 0; h2 < 5; ++h2) {
+                const double2 m2 = __ldg(row + h2);
+                tau[2 * h2] = fma(m2.x, val, tau[2 * h2]);
+                if (h2 < 4) tau[2 * h2 + 1] = fma(m2.y, val, tau[2 * h2 + 1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) tau[i] *= -mu;
+}
+
+// One warp = one facet x one time segment; the 32 lanes are 32 consecutive columns of the staged block.
 // MULTI = false: facets whose cell owns no other exterior facet (work[0, multi_start)); MULTI = true: the rest.
 template <int ORDER, bool MULTI>
-__global__ void __launch_bounds__(32 * K2_WARPS) k2_wall(const K2Args a) {
+__global__ void __launch_bounds__(32 * K2_WARPS, (ORDER == 2 || MULTI) ? 3 : 4) k2_wall(const K2Args a) {
+    extern __shared__ __align__(16) double k2_smem[];
+    constexpr int N = Dofs<ORDER>::N;
+    constexpr bool RING = ORDER == 2;  // cp.async shared-memory ring (else: register double buffer)
     const FacetTables& T = a.T;
     const int64_t nF = T.nF;
-    const int lane = threadIdx.x & 31;
-    const int64_t wi = (int64_t)blockIdx.x * K2_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t wi = (int64_t)blockIdx.x * K2_WARPS + wib;
     const int64_t w = MULTI ? wi + T.multi_start : wi;
     if (w >= (MULTI ? T.n_work : T.multi_start)) return;
     const int32_t f = T.work[w];
@@ -240,34 +230,100 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_wall(const K2Args a) {
     constexpr bool FLAT = (ORDER == 1) && !MULTI;
     constexpr int NT = FLAT ? 3 : 9;
 
-    int64_t base[10];
-    double g[4][3], n[3], gam[4];
-#pragma unroll
-    for (int k = 0; k < Dofs<ORDER>::N; ++k) base[k] = 3 * (int64_t)T.row[(int64_t)k * nF + f] * a.ld;
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-#pragma unroll
-        for (int d = 0; d < 3; ++d) g[b][d] = T.glam[(int64_t)(3 * b + d) * nF + f];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) n[d] = T.normal[(int64_t)d * nF + f];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) gam[b] = g[b][0] * n[0] + g[b][1] * n[1] + g[b][2] * n[2];
+    const int y = blockIdx.y;
+    const int pass0 = y * a.pass_base + min(y, a.pass_extra);
+    const int npass = a.pass_base + (y < a.pass_extra ? 1 : 0);
+    const int seg0 = a.r0 + pass0 * K2_COLS;  // first real column of this segment
+    const int seg1 = min(seg0 + npass * K2_COLS, a.ncol);
 
-    const int seg0 = a.r0 + (int)blockIdx.y * a.seg_len;  // first real column of this segment
-    const int seg1 = min(seg0 + a.seg_len, a.ncol);
+    // x-component row of every cell dof (y, z follow at +ld, +2 ld), already offset to this lane's first column
+    const double* rp[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+        rp[k] = a.W + 3 * (int64_t)T.row[(int64_t)k * nF + f] * a.ld + (seg0 + lane - 1);
+    const int64_t ld = a.ld;
+    // column offset of pass j relative to rp: the lane's column is clamped into [0, seg1)
+    auto pass_off = [&](int j) {
+        const int col = seg0 + j * K2_COLS + lane - 1;
+        return min(max(col, 0), seg1 - 1) - (seg0 + lane - 1);
+    };
+
+    double* const ring = k2_smem + (size_t)wib * 2 * 3 * N * 32 + lane;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    Vel vn;  // register double buffer (P1)
+    auto prefetch = [&](int j) {
+        const int off = pass_off(j);
+        if (RING) {
+            const uint32_t dst = ring_s + (uint32_t)((j & 1) * 3 * N * 32 * sizeof(double));
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                const double* p = rp[k] + off;
+                cp_async8(dst + (3 * k + 0) * 256, p);
+                cp_async8(dst + (3 * k + 1) * 256, p + ld);
+                cp_async8(dst + (3 * k + 2) * 256, p + 2 * ld);
+            }
+            cp_async_commit();
+        } else {
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                const double* p = rp[k] + off;
+                vn.x[k] = __ldg(p);
+                vn.y[k] = __ldg(p + ld);
+                vn.z[k] = __ldg(p + 2 * ld);
+            }
+        }
+    };
+    prefetch(0);
+
+    double g[4][3], n[3], gam[4];
+    const double* M = nullptr;
+    if (MULTI) {
+        M = T.m_mat + (size_t)wi * 3 * N * VH_MROW;
+    } else {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) g[b][d] = T.glam[(int64_t)(3 * b + d) * nF + f];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) n[d] = T.normal[(int64_t)d * nF + f];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) gam[b] = g[b][0] * n[0] + g[b][1] * n[1] + g[b][2] * n[2];
+    }
 
     double acc[VH_NSUM];
 #pragma unroll
     for (int i = 0; i < VH_NSUM; ++i) acc[i] = 0.0;
 
-    for (int c0 = seg0; c0 < seg1; c0 += K2_COLS) {
-        const int col = c0 + lane - 1;  // lane 0: the column before this pass
-        const bool live = lane > 0 && col < seg1;
+    for (int j = 0; j < npass; ++j) {
         Vel v;
-        load_vel<ORDER>(a.W, base, a.ld, min(max(col, 0), seg1 - 1), v);
+        if (RING) {
+            if (j + 1 < npass) {
+                prefetch(j + 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            const double* sv = ring + (j & 1) * 3 * N * 32;
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                v.x[k] = sv[(3 * k + 0) * 32];
+                v.y[k] = sv[(3 * k + 1) * 32];
+                v.z[k] = sv[(3 * k + 2) * 32];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                v.x[k] = vn.x[k];
+                v.y[k] = vn.y[k];
+                v.z[k] = vn.z[k];
+            }
+            if (j + 1 < npass) prefetch(j + 1);
+        }
+        const int col = seg0 + j * K2_COLS + lane - 1;  // lane 0: the column before this pass
+        const bool live = lane > 0 && col < seg1;
         double tau[9];
         if (MULTI)
-            tau_multi<ORDER>(g, v, a.mu, T.m_lf, T.m_w, wi, T.nMulti, tau);
+            tau_dense<ORDER>(M, v, a.mu, tau);
         else
             tau_single<ORDER>(g, n, gam, v, a.mu, tau);
         if (col < 0) {  // no column before the block's first: tau_prev is zero or carried over from the last launch
@@ -290,10 +346,10 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_wall(const K2Args a) {
 #pragma unroll
                 for (int i = 0; i < 9; ++i) acc[i] += tau[i];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) acc[9 + j] += norm3(tau[3 * j], tau[3 * j + 1], tau[3 * j + 2]);
+                for (int j2 = 0; j2 < 3; ++j2) acc[9 + j2] += norm3(tau[3 * j2], tau[3 * j2 + 1], tau[3 * j2 + 2]);
                 twssg_project(dw, p);
 #pragma unroll
-                for (int j = 0; j < 3; ++j) acc[12 + j] += p[j];
+                for (int j2 = 0; j2 < 3; ++j2) acc[12 + j2] += p[j2];
             }
             if (a.wss_out) {
                 double* o = a.wss_out + ((int64_t)(col - a.r0) * nF + f) * 9;
@@ -321,19 +377,28 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_wall(const K2Args a) {
         acc[13] = acc[14] = acc[12];
     }
     if (lane == 0) {
-        double* p = a.part + (int64_t)blockIdx.y * VH_NSUM * nF + f;
+        double* p = a.part + (int64_t)y * VH_NSUM * T.n_work + w;
 #pragma unroll
-        for (int i = 0; i < VH_NSUM; ++i) p[(int64_t)i * nF] = acc[i];
+        for (int i = 0; i < VH_NSUM; ++i) p[(int64_t)i * T.n_work] = acc[i];
     }
 }
 
-// sums[r][f] += part[0][r][f] + part[1][r][f] + ...   (fixed order)
-__global__ void k3_fold(double* __restrict__ sums, const double* __restrict__ part, int64_t n, int64_t groups) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double t = sums[i];
-    for (int64_t gq = 0; gq < groups; ++gq) t += part[gq * n + i];
-    sums[i] = t;
+// sums[i][f] += part[0][i][w] + part[1][i][w] + ...  for f = work[w], in fixed order; the single-facet and the
+// multi-facet launches have their own segment counts and partial-sum blocks
+__global__ void k3_fold(double* __restrict__ sums, const double* __restrict__ part_s, int gy_s,
+                        const double* __restrict__ part_m, int gy_m, const int32_t* __restrict__ work, int64_t n_work,
+                        int64_t multi_start, int64_t nF) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= VH_NSUM * n_work) return;
+    const int64_t w = idx % n_work, i = idx / n_work;
+    const int32_t f = work[w];
+    if (f < 0) return;
+    const bool multi = w >= multi_start;
+    const double* p = (multi ? part_m : part_s) + i * n_work + w;
+    const int gq = multi ? gy_m : gy_s;
+    double t = sums[i * nF + f];
+    for (int q = 0; q < gq; ++q) t += p[(int64_t)q * VH_NSUM * n_work];
+    sums[i * nF + f] = t;
 }
 
 // compute_hemodynamics.py:326-346
@@ -369,8 +434,7 @@ FacetTables vh_tables(const vh_handle* h) {
     T.work = h->d_work;
     T.n_work = h->n_work;
     T.multi_start = h->multi_start;
-    T.m_lf = h->d_m_lf;
-    T.m_w = h->d_m_w;
+    T.m_mat = h->d_m_mat;
     T.nMulti = h->nMulti;
     return T;
 }
@@ -421,6 +485,43 @@ static int ensure_stage_block(vh_handle* h, int64_t want_cols) {
     return VH_OK;
 }
 
+namespace {
+
+// Segments of one launch: `total` lane passes split as evenly as possible over gy segments.
+struct SegPlan {
+    int gy, base, extra;
+};
+
+SegPlan plan_segments(int64_t nb, int64_t n_items, int64_t target_warps, int64_t chunk_snapshots) {
+    const int64_t total = (nb + K2_COLS - 1) / K2_COLS;
+    int64_t gy;
+    if (chunk_snapshots > 0) {
+        const int64_t p = (chunk_snapshots + K2_COLS - 1) / K2_COLS;
+        gy = (total + p - 1) / p;
+    } else {
+        gy = n_items > 0 ? (target_warps + n_items - 1) / n_items : 1;
+    }
+    if (gy < 1) gy = 1;
+    if (gy > total) gy = total;
+    if (gy > 65535) gy = 65535;
+    return {(int)gy, (int)(total / gy), (int)(total % gy)};
+}
+
+template <int ORDER, bool MULTI>
+int launch_k2(const K2Args& a, unsigned gx, unsigned gy, cudaStream_t st) {
+    constexpr int smem = k2_smem_bytes<ORDER>();
+    static bool configured = false;  // per instantiation
+    if (!configured && smem > 48 * 1024) {
+        VH_CUDA(cudaFuncSetAttribute(k2_wall<ORDER, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    k2_wall<ORDER, MULTI><<<dim3(gx, gy), 32 * K2_WARPS, smem, st>>>(a);
+    VH_CUDA(cudaGetLastError());
+    return VH_OK;
+}
+
+}  // namespace
+
 int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_elems, int prev_mode, double* d_wss) {
     if (n_snap <= 0) return VH_OK;
     const int64_t nF = h->nF;
@@ -434,24 +535,20 @@ int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_el
         int64_t nb = n_snap - pos;
         if (nb + halo > h->w_ld) nb = h->w_ld - halo;
         const int64_t ncol = nb + halo;
-        // segment length = p lane passes of 31 real snapshots: the fewest segments that still give every SM ~64
-        // (facet, segment) warps to schedule
-        int64_t p = (h->chunk_snapshots + K2_COLS - 1) / K2_COLS;
-        if (p <= 0) {
-            const int64_t target_warps = (int64_t)h->sm_count * 64;
-            for (p = (nb + K2_COLS - 1) / K2_COLS; p > 1; --p)
-                if (h->n_work * ((nb + K2_COLS * p - 1) / (K2_COLS * p)) >= target_warps) break;
-        }
-        const int64_t seg = K2_COLS * p;
-        const int64_t gy = (nb + seg - 1) / seg;
-        VH_CHECK(gy <= 65535, VH_ERR_ARG, "k2_launch: too many segments (%lld); raise chunk_snapshots", (long long)gy);
-        if (gy > h->part_cap) {
+        // the fewest segments that still give every SM ~64 (facet, segment) warps to schedule; the few multi-facet-cell
+        // facets run beside them on a second stream, cut finer so that they never become the tail
+        const SegPlan ps = plan_segments(nb, n_single, (int64_t)h->sm_count * 64, h->chunk_snapshots);
+        const SegPlan pm = plan_segments(nb, n_multi, (int64_t)h->sm_count * 16, h->chunk_snapshots);
+        const int64_t groups = ps.gy + (n_multi ? pm.gy : 0);
+        if (groups > h->part_cap) {
             if (h->d_part) cudaFree(h->d_part);
             h->d_part = nullptr;
             h->part_cap = 0;
-            VH_CUDA(cudaMalloc(&h->d_part, sizeof(double) * VH_NSUM * nF * gy));
-            h->part_cap = gy;
+            VH_CUDA(cudaMalloc(&h->d_part, sizeof(double) * VH_NSUM * h->n_work * groups));
+            h->part_cap = groups;
         }
+        double* part_s = h->d_part;
+        double* part_m = h->d_part + (int64_t)ps.gy * VH_NSUM * h->n_work;
         const bool prof = h->profile && h->prof_used + 3 <= h->prof_pool.size();
         if (prof) cudaEventRecord(h->prof_pool[h->prof_used], h->s_compute);
         VH_TRY(k1_launch(h, d_u + (pos - halo) * stride_elems, ncol, stride_elems));
@@ -462,39 +559,44 @@ int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_el
         a.ld = h->w_ld;
         a.ncol = (int)ncol;
         a.r0 = halo;
-        a.seg_len = (int)seg;
         a.prev_mode = pos == 0 ? prev_mode : 1;
         a.tau_last_in = h->d_tau_last[h->tau_cur];
         a.tau_last_out = h->d_tau_last[h->tau_cur ^ 1];
         h->tau_cur ^= 1;
-        a.part = h->d_part;
         a.wss_out = d_wss ? d_wss + pos * nF * 9 : nullptr;
         a.mu = h->mu;
         a.inv_dt = 1.0 / h->dt;
-        dim3 block(32 * K2_WARPS);
+        if (gx_multi) {  // fork: multi-facet cells on the auxiliary stream, after K1
+            VH_CUDA(cudaEventRecord(h->ev_fork, h->s_compute));
+            VH_CUDA(cudaStreamWaitEvent(h->s_aux, h->ev_fork, 0));
+            a.part = part_m;
+            a.pass_base = pm.base;
+            a.pass_extra = pm.extra;
+            if (h->order == 2)
+                VH_TRY((launch_k2<2, true>(a, gx_multi, pm.gy, h->s_aux)));
+            else
+                VH_TRY((launch_k2<1, true>(a, gx_multi, pm.gy, h->s_aux)));
+            VH_CUDA(cudaEventRecord(h->ev_join, h->s_aux));
+            h->launches += 1;
+        }
         if (gx_single) {
-            dim3 grid(gx_single, (unsigned)gy);
+            a.part = part_s;
+            a.pass_base = ps.base;
+            a.pass_extra = ps.extra;
             if (h->order == 2)
-                k2_wall<2, false><<<grid, block, 0, h->s_compute>>>(a);
+                VH_TRY((launch_k2<2, false>(a, gx_single, ps.gy, h->s_compute)));
             else
-                k2_wall<1, false><<<grid, block, 0, h->s_compute>>>(a);
+                VH_TRY((launch_k2<1, false>(a, gx_single, ps.gy, h->s_compute)));
             h->launches += 1;
         }
-        if (gx_multi) {
-            dim3 grid(gx_multi, (unsigned)gy);
-            if (h->order == 2)
-                k2_wall<2, true><<<grid, block, 0, h->s_compute>>>(a);
-            else
-                k2_wall<1, true><<<grid, block, 0, h->s_compute>>>(a);
-            h->launches += 1;
-        }
+        if (gx_multi) VH_CUDA(cudaStreamWaitEvent(h->s_compute, h->ev_join, 0));
         if (prof) {
             cudaEventRecord(h->prof_pool[h->prof_used + 2], h->s_compute);
             h->prof_used += 3;
         }
-        VH_CUDA(cudaGetLastError());
-        const int64_t n = VH_NSUM * nF;
-        k3_fold<<<(unsigned)((n + 255) / 256), 256, 0, h->s_compute>>>(h->d_sums, h->d_part, n, gy);
+        const int64_t n = VH_NSUM * h->n_work;
+        k3_fold<<<(unsigned)((n + 255) / 256), 256, 0, h->s_compute>>>(h->d_sums, part_s, gx_single ? ps.gy : 0, part_m,
+                                                                       pm.gy, h->d_work, h->n_work, h->multi_start, nF);
         VH_CUDA(cudaGetLastError());
         h->launches += 1;
         pos += nb;
