@@ -193,52 +193,59 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     nF, vec_len = eng.nF, eng.vec_len
     comm = NcclComm(eng, rank, world) if world > 1 else None
 
-    # inputs: pinned host copy (e2e) and a resident device copy (value)
+    # inputs: pinned host copy (e2e) and resident device copies (value).  Timing rule: inputs must not be served from
+    # L2 across timed steps.  A workload smaller than 2x the 126 MB L2 gets enough rotating copies to exceed 2.5x L2
+    # (consecutive steps read different copies, so the K steps run back to back with no flush kernel and no host
+    # synchronisation in the timed region); larger workloads evict themselves.
     u_host = pinned_empty((n_snap + halo, vec_len))
     synth.velocity_series(wl["basis"], wl["coef"], out=u_host)
-    d_u = eng.device_alloc(u_host.nbytes)
-    eng.h2d(d_u, u_host)
+    L2 = 126e6
+    n_copies = 1 if u_host.nbytes >= 2 * L2 else min(8, int(np.ceil(2.5 * L2 / u_host.nbytes)))
+    d_copies = []
+    for _ in range(n_copies):
+        d = eng.device_alloc(u_host.nbytes)
+        eng.h2d(d, u_host)
+        d_copies.append(d)
     flags = 2 if halo else 1
     stride = vec_len * 8
     n_total = n_snap * world
+    step_no = [0]
 
     def step_resident():
+        d_u = d_copies[step_no[0] % n_copies]
+        step_no[0] += 1
         eng.begin(MU, wl["dt"])
         eng.push_device(d_u, n_snap + halo, stride, flags)
         if comm:
-            comm.allreduce_sums()
-        eng.finalize_async(n_total)
+            comm.reduce_finalize(n_total, host=False)  # fused peer reduction + K4 (or ncclAllReduce + K4)
+        else:
+            eng.finalize_async(n_total)
 
     def step_e2e():
         eng.begin(MU, wl["dt"])
         eng.push(u_host, flags=flags)
         if comm:
-            comm.allreduce_sums()
+            return comm.reduce_finalize(n_total)
         return eng.finalize(n_total)
 
     for _ in range(args.warmup):
-        eng.flush_l2()
         step_resident()
     eng.sync()
-    if comm:
-        comm.barrier()
     eng.set_profile(True)
     launches0 = eng.timers()["launches"]
-    step_ms = []
+    if comm:
+        comm.barrier()
     with ClockSampler(local_rank) as clk:
-        for _ in range(args.steps):
-            eng.flush_l2()          # inputs (72 MB here) are smaller than the 126 MB L2: evict between steps
-            eng.sync()
-            eng.timer_start()
-            step_resident()
-            step_ms.append(eng.timer_stop())
         eng.sync()
+        eng.timer_start()
+        for _ in range(args.steps):
+            step_resident()
+        total_ms = eng.timer_stop()  # CUDA events on the compute stream; stop synchronises
     if comm:
         comm.barrier()
     k1_ms, k2_ms, k2_n = eng.kernel_profile()
     eng.set_profile(False)
     launches = eng.timers()["launches"] - launches0  # k1 + k2 (+ k2 multi) + k3 + k4 per step (L2 flush not counted)
-    total_ms = float(np.sum(step_ms))
     if comm:
         total_ms = comm.max(total_ms)
     ms_per_step = total_ms / args.steps
@@ -263,8 +270,9 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     osi = out["OSI"]
     sane = bool(np.isfinite(out["TAWSS"]).all() and np.nanmin(osi) >= -1e-12 and np.nanmax(osi) <= 0.5 + 1e-12)
 
+    for d in d_copies:
+        eng.device_free(d)
     if rank != 0:
-        eng.device_free(d_u)
         return
     peak, peak_src = measured_peak_gbs()
     b_alg = algorithmic_bytes_per_unit(order)
@@ -292,7 +300,12 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         "config": {"workload": f"{args.workload}: {wl['desc']}", "facets": nF, "snapshots_per_gpu": n_snap,
                    "order": order, "velocity_nodes": int(len(wl["points"])), "wall_layer_nodes": eng.n_wall_nodes,
                    "tets": int(len(wl["tets"])),
-                   "parallelism": f"time-shard x{world}", "l2": "flushed between timed steps (512 MiB write)",
+                   "parallelism": f"time-shard x{world}",
+                   "reduction": ("none" if not comm else "fused peer-memory reduce+finalize (NVLink, CUDA IPC)"
+                                 if comm.fused else "ncclAllReduce + finalize"), 
+                   "l2": (f"{n_copies} rotating resident copies of the input ({n_copies * u_host.nbytes / 1e6:.0f} MB > "
+                          f"2.5 x 126 MB L2), steps back to back" if n_copies > 1 else
+                          f"input {u_host.nbytes / 1e6:.0f} MB per step, larger than 2 x 126 MB L2"),
                    "results_sane": sane},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
@@ -310,7 +323,6 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
-    eng.device_free(d_u)
 
 
 def cpu_baseline(wl, n_snap: int):

@@ -149,6 +149,17 @@ int vh_nccl_allreduce_max(vh_handle* h, double* value);
 int vh_nccl_barrier(vh_handle* h);
 int vh_nccl_destroy(vh_handle* h);
 
+/* Fused reduction + final formulas over NVLink peer memory (all ranks on one NVSwitch node, <= 8).
+ * vh_peer_init (collective; after vh_nccl_init, vh_set_mesh and vh_set_velocity_layout on every rank) maps every
+ * rank's running sums into this process with CUDA IPC.  vh_peer_reduce_finalize (collective) then replaces
+ * vh_nccl_allreduce_sums + vh_finalize by ONE kernel per rank: it waits for every rank's arrival counter, adds the
+ * 15*nF partial sums of all ranks in rank order straight from their memory (bitwise identical on every rank) and
+ * evaluates :326-346.  Stream-ordered, no host synchronisation unless host outputs are requested.  If peer memory
+ * cannot be mapped vh_peer_init fails on every rank and the NCCL path above remains. */
+int vh_peer_init(vh_handle* h);
+int vh_peer_reduce_finalize(vh_handle* h, int64_t n_total, double* tawss, double* osi, double* rrt, double* ecap,
+                            double* twssg);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,8 @@ _SIGNATURES = {
     "vh_nccl_allreduce_max": [_P, C.POINTER(_DBL)],
     "vh_nccl_barrier": [_P],
     "vh_nccl_destroy": [_P],
+    "vh_peer_init": [_P],
+    "vh_peer_reduce_finalize": [_P, _I64, _P, _P, _P, _P, _P],
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(list(_SIGNATURES) + ["vh_last_error"]))

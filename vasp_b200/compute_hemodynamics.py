@@ -213,8 +213,7 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
     if shard_file is not None:
         shard_file.flush()
         del shard_file
-    if comm is not None:
-        comm.allreduce_sums()  # the single collective: 15*nF partial sums + the snapshot count
+    # the single collective (15*nF partial sums + the snapshot count) happens below, fused with the final formulas
 
     if rank == 0:
         # WSS of the other ranks' time ranges, in order
@@ -230,7 +229,7 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
         wss_writer.close()
         print("=" * 10, "Saving hemodynamic indices", "=" * 10)
 
-    out = eng.finalize(n_snap)
+    out = comm.reduce_finalize(n_snap) if comm is not None else eng.finalize(n_snap)
     timers = eng.timers()
     series.close()
     if rank == 0:

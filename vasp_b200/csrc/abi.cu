@@ -25,6 +25,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 } g_nccl;
@@ -43,6 +44,7 @@ int nccl_load() {
     VH_SYM(GetUniqueId, "ncclGetUniqueId");
     VH_SYM(CommInitRank, "ncclCommInitRank");
     VH_SYM(AllReduce, "ncclAllReduce");
+    VH_SYM(AllGather, "ncclAllGather");
     VH_SYM(CommDestroy, "ncclCommDestroy");
     VH_SYM(GetErrorString, "ncclGetErrorString");
 #undef VH_SYM
@@ -60,11 +62,27 @@ int nccl_load() {
 
 int ensure_run_buffers(vh_handle* h) {
     const int64_t nF = h->nF;
-    if (!h->d_sums) {
-        VH_CUDA(cudaMalloc(&h->d_sums, sizeof(double) * (VH_NSUM * nF + 1)));  // + the snapshot count (all-reduce)
+    if (!h->d_sums_block) {
+        // two halves of (15 nF sums + the snapshot count), then the arrival counters of the peer reduction
+        h->sum_stride = (VH_NSUM * nF + 1 + 15) / 16 * 16;
+        const size_t bytes = sizeof(double) * (2 * h->sum_stride + VH_MAX_PEERS);
+        VH_CUDA(cudaMalloc(&h->d_sums_block, bytes));
+        VH_CUDA(cudaMemset(h->d_sums_block, 0, bytes));
+        VH_CUDA(cudaMalloc(&h->d_sums_red, sizeof(double) * (VH_NSUM * nF + 1)));
+        h->loop_parity = 0;
+        h->d_sums = h->d_sums_block;
         VH_CUDA(cudaMalloc(&h->d_tau_last[0], sizeof(double) * 9 * nF));
         VH_CUDA(cudaMalloc(&h->d_tau_last[1], sizeof(double) * 9 * nF));
         VH_CUDA(cudaMalloc(&h->d_out5, sizeof(double) * 15 * nF));
+    }
+    return VH_OK;
+}
+
+// the running sums are zeroed lazily (see vh_begin); anyone who reads them before the first push calls this
+int settle_sums(vh_handle* h) {
+    if (h->sums_pending_zero) {
+        VH_CUDA(cudaMemsetAsync(h->d_sums, 0, sizeof(double) * (VH_NSUM * h->nF + 1), h->s_compute));
+        h->sums_pending_zero = false;
     }
     return VH_OK;
 }
@@ -84,6 +102,16 @@ __global__ void k_flush(double* __restrict__ p, int64_t n, double v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t step = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += step) p[i] = v;
+}
+
+// second half of the flush: stream a buffer larger than L2 through it so that the cache is left full of CLEAN
+// foreign lines (a write-only flush leaves 126 MB of dirty lines whose write-back would be billed to the next kernel)
+__global__ void k_flush_read(const double* __restrict__ p, int64_t n, double* __restrict__ sink) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t step = (int64_t)gridDim.x * blockDim.x;
+    double t = 0.0;
+    for (; i < n; i += step) t += p[i];
+    if (t == 12345.678) *sink = t;  // never true; keeps the loads alive
 }
 
 }  // namespace
@@ -242,9 +270,12 @@ int vh_begin(vh_handle* h, double mu, double dt) {
     h->count_on_device = false;
     h->have_tau_last = false;
     h->kernel_ms = h->h2d_ms = 0.0;
-    VH_CUDA(cudaMemsetAsync(h->d_sums, 0, sizeof(double) * (VH_NSUM * h->nF + 1), h->s_compute));
-    VH_CUDA(cudaMemsetAsync(h->d_tau_last[0], 0, sizeof(double) * 9 * h->nF, h->s_compute));
-    VH_CUDA(cudaMemsetAsync(h->d_tau_last[1], 0, sizeof(double) * 9 * h->nF, h->s_compute));
+    // no memsets on the hot path: the first K3 of the loop overwrites the sums instead of adding to them, and
+    // tau_last is only read after a launch has written it
+    h->sums_pending_zero = true;
+    h->sums_reduced = false;
+    h->loop_parity ^= 1;  // alternate halves of the peer-visible block (see common.cuh)
+    h->d_sums = h->d_sums_block + (int64_t)h->loop_parity * h->sum_stride;
     h->begun = true;  // stream-ordered: no host sync needed before the first push
     return VH_OK;
 }
@@ -413,11 +444,13 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
 
 int vh_get_sums(vh_handle* h, double* sums, int64_t* count) {
     VH_TRY(check_ready(h, "vh_get_sums"));
+    VH_TRY(settle_sums(h));
     VH_CUDA(cudaStreamSynchronize(h->s_compute));
-    if (sums) VH_CUDA(cudaMemcpy(sums, h->d_sums, sizeof(double) * VH_NSUM * h->nF, cudaMemcpyDeviceToHost));
-    if (h->count_on_device) {  // left there by vh_nccl_allreduce_sums, which does not synchronise
+    const double* src = h->sums_reduced ? h->d_sums_red : h->d_sums;  // after a fused peer reduction: the global sums
+    if (sums) VH_CUDA(cudaMemcpy(sums, src, sizeof(double) * VH_NSUM * h->nF, cudaMemcpyDeviceToHost));
+    if (h->count_on_device) {  // left there by the all-reduce / peer reduction, which do not synchronise
         double cnt = 0.0;
-        VH_CUDA(cudaMemcpy(&cnt, h->d_sums + VH_NSUM * h->nF, sizeof(double), cudaMemcpyDeviceToHost));
+        VH_CUDA(cudaMemcpy(&cnt, src + VH_NSUM * h->nF, sizeof(double), cudaMemcpyDeviceToHost));
         h->count = (int64_t)(cnt + 0.5);
         h->count_on_device = false;
     }
@@ -428,6 +461,8 @@ int vh_get_sums(vh_handle* h, double* sums, int64_t* count) {
 int vh_set_sums(vh_handle* h, const double* sums, int64_t count) {
     VH_TRY(check_ready(h, "vh_set_sums"));
     VH_CHECK(sums, VH_ERR_ARG, "vh_set_sums: null sums");
+    h->sums_pending_zero = false;
+    h->sums_reduced = false;
     VH_CUDA(cudaStreamSynchronize(h->s_compute));
     VH_CUDA(cudaMemcpy(h->d_sums, sums, sizeof(double) * VH_NSUM * h->nF, cudaMemcpyHostToDevice));
     h->count = count;
@@ -437,6 +472,7 @@ int vh_set_sums(vh_handle* h, const double* sums, int64_t count) {
 
 int vh_sums_device_ptr(vh_handle* h, double** d_sums) {
     VH_TRY(check_ready(h, "vh_sums_device_ptr"));
+    VH_TRY(settle_sums(h));
     *d_sums = h->d_sums;
     return VH_OK;
 }
@@ -456,6 +492,7 @@ int vh_get_tau_last(vh_handle* h, double* tau) {
 int vh_finalize(vh_handle* h, int64_t n_total, double* tawss, double* osi, double* rrt, double* ecap, double* twssg) {
     VH_TRY(check_ready(h, "vh_finalize"));
     VH_CHECK(n_total > 0, VH_ERR_ARG, "vh_finalize: n_total must be positive");
+    VH_TRY(settle_sums(h));
     const int64_t n3 = 3 * h->nF;
     VH_TRY(k4_finalize(h, n_total, h->d_out5));
     double* outs[5] = {tawss, osi, rrt, ecap, twssg};
@@ -580,12 +617,15 @@ int vh_flush_l2(vh_handle* h) {
     VH_CHECK(h, VH_ERR_ARG, "vh_flush_l2: null handle");
     VH_CUDA(cudaSetDevice(h->device));
     if (!h->d_flush) {
-        h->flush_bytes = 512LL << 20;  // 4x the 126 MB L2
+        h->flush_bytes = 512LL << 20;  // two halves of 256 MiB, each 2x the 126 MB L2: one written, one read
+        
         VH_CUDA(cudaMalloc(&h->d_flush, (size_t)h->flush_bytes));
     }
     static double tick = 0.0;
     tick += 1.0;
-    k_flush<<<h->sm_count * 8, 256, 0, h->s_compute>>>((double*)h->d_flush, h->flush_bytes / 8, tick);
+    const int64_t half = h->flush_bytes / 16;  // doubles in each half of the scratch buffer
+    k_flush<<<h->sm_count * 8, 256, 0, h->s_compute>>>((double*)h->d_flush, half, tick);
+    k_flush_read<<<h->sm_count * 8, 256, 0, h->s_compute>>>((const double*)h->d_flush + half, half, (double*)h->d_flush);
     VH_CUDA(cudaGetLastError());
     return VH_OK;
 }
@@ -630,6 +670,7 @@ int vh_nccl_init(vh_handle* h, const char id[128], int rank, int world) {
 int vh_nccl_allreduce_sums(vh_handle* h) {
     VH_TRY(check_ready(h, "vh_nccl_allreduce_sums"));
     VH_CHECK(h->nccl_comm, VH_ERR_NCCL, "vh_nccl_allreduce_sums: call vh_nccl_init first");
+    VH_TRY(settle_sums(h));
     // one collective, stream-ordered, no host synchronisation: the snapshot count rides behind the 15 * nF sums
     const int64_t n = VH_NSUM * h->nF;
     if (!h->count_on_device) {
@@ -659,7 +700,108 @@ int vh_nccl_barrier(vh_handle* h) {
     return vh_nccl_allreduce_max(h, &v);
 }
 
+static void peer_close(vh_handle* h) {
+    for (int q = 0; q < VH_MAX_PEERS; ++q) {
+        if (h->peer_block[q] && q != h->rank) cudaIpcCloseMemHandle(h->peer_block[q]);
+        h->peer_block[q] = nullptr;
+    }
+    h->peer_ready = false;
+}
+
+int vh_peer_init(vh_handle* h) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_peer_init: null handle");
+    VH_CUDA(cudaSetDevice(h->device));
+    VH_CHECK(h->nccl_comm, VH_ERR_NCCL, "vh_peer_init: call vh_nccl_init first (it carries the handle exchange)");
+    VH_CHECK(h->nF > 0 && h->order != 0, VH_ERR_ARG, "vh_peer_init: set mesh and velocity layout first");
+    VH_CHECK(h->world <= VH_MAX_PEERS, VH_ERR_ARG, "vh_peer_init: at most %d ranks", VH_MAX_PEERS);
+    peer_close(h);
+    VH_TRY(ensure_run_buffers(h));
+    VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    cudaIpcMemHandle_t mine;
+    VH_CUDA(cudaIpcGetMemHandle(&mine, h->d_sums_block));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    // every rank also publishes sum_stride: all ranks must have built the same mesh
+    struct Card {
+        cudaIpcMemHandle_t handle;
+        int64_t stride;
+    } card{mine, h->sum_stride};
+    char *d_send = nullptr, *d_recv = nullptr;
+    VH_CUDA(cudaMalloc(&d_send, sizeof(Card)));
+    VH_CUDA(cudaMalloc(&d_recv, sizeof(Card) * h->world));
+    VH_CUDA(cudaMemcpyAsync(d_send, &card, sizeof(Card), cudaMemcpyHostToDevice, h->s_compute));
+    VH_NCCL(g_nccl.AllGather(d_send, d_recv, sizeof(Card), ncclChar, (ncclComm_t)h->nccl_comm, h->s_compute));
+    std::vector<Card> all(h->world);
+    VH_CUDA(cudaMemcpyAsync(all.data(), d_recv, sizeof(Card) * h->world, cudaMemcpyDeviceToHost, h->s_compute));
+    VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    cudaFree(d_send);
+    cudaFree(d_recv);
+    int rc = VH_OK;
+    for (int q = 0; q < h->world && rc == VH_OK; ++q) {
+        if (all[q].stride != h->sum_stride) {
+            vh_set_error("vh_peer_init: rank %d has a different mesh (%lld vs %lld sums)", q, (long long)all[q].stride,
+                         (long long)h->sum_stride);
+            rc = VH_ERR_ARG;
+        } else if (q == h->rank) {
+            h->peer_block[q] = h->d_sums_block;
+        } else {
+            void* p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, all[q].handle, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                vh_set_error("vh_peer_init: cannot map rank %d's sums (%s); use vh_nccl_allreduce_sums", q,
+                             cudaGetErrorString(e));
+                cudaGetLastError();
+                rc = VH_ERR_CUDA;
+            } else {
+                h->peer_block[q] = (double*)p;
+            }
+        }
+    }
+    // agree on the outcome (a rank that failed must not leave the others spinning later) and make sure every
+    // rank's counters are zeroed before anyone signals
+    double ok = rc == VH_OK ? 0.0 : 1.0;
+    int rc2 = vh_nccl_allreduce_max(h, &ok);
+    if (rc == VH_OK && rc2 != VH_OK) rc = rc2;
+    if (rc == VH_OK && ok != 0.0) {
+        vh_set_error("vh_peer_init: another rank could not map peer memory; use vh_nccl_allreduce_sums");
+        rc = VH_ERR_CUDA;
+    }
+    if (rc != VH_OK) {
+        peer_close(h);
+        return rc;
+    }
+    h->peer_epoch = 0;
+    h->peer_ready = true;
+    return VH_OK;
+}
+
+int vh_peer_reduce_finalize(vh_handle* h, int64_t n_total, double* tawss, double* osi, double* rrt, double* ecap,
+                            double* twssg) {
+    VH_TRY(check_ready(h, "vh_peer_reduce_finalize"));
+    VH_CHECK(h->peer_ready, VH_ERR_ARG, "vh_peer_reduce_finalize: call vh_peer_init first");
+    VH_CHECK(n_total > 0, VH_ERR_ARG, "vh_peer_reduce_finalize: n_total must be positive");
+    VH_TRY(settle_sums(h));
+    const int64_t n3 = 3 * h->nF;
+    PeerBlocks pb;
+    for (int q = 0; q < VH_MAX_PEERS; ++q) pb.block[q] = h->peer_block[q];
+    const int64_t half_off = (int64_t)h->loop_parity * h->sum_stride, flags_off = 2 * h->sum_stride;
+    h->peer_epoch += 1;
+    VH_TRY(k4_peer_signal(h, pb, flags_off, h->peer_epoch));
+    VH_TRY(k4_peer_reduce_finalize(h, pb, half_off, flags_off, h->peer_epoch, n_total, h->d_sums_red, h->d_out5));
+    h->sums_reduced = true;
+    h->count_on_device = true;
+    double* outs[5] = {tawss, osi, rrt, ecap, twssg};
+    bool any = false;
+    for (int i = 0; i < 5; ++i) {
+        if (!outs[i]) continue;
+        any = true;
+        VH_CUDA(cudaMemcpyAsync(outs[i], h->d_out5 + i * n3, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->s_compute));
+    }
+    if (any) VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    return VH_OK;
+}
+
 int vh_nccl_destroy(vh_handle* h) {
+    if (h) peer_close(h);
     if (h && h->nccl_comm && g_nccl.CommDestroy) {
         g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
         h->nccl_comm = nullptr;

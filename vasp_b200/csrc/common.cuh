@@ -37,6 +37,7 @@ void vh_set_error(const char* fmt, ...);
 // Number of running sums per facet: 9 (sum tau) + 3 (sum |tau|) + 3 (sum P(|dtau/dt|)); SoA rows of length nF.
 constexpr int VH_NSUM = 15;
 constexpr int VH_MAX_CONTRIB = 4;  // a tet has at most 4 exterior facets
+constexpr int VH_MAX_PEERS = 8;     // GPUs of one NVSwitch node
 constexpr int VH_MROW = 10;        // row length of the multi-facet operator: 9 outputs padded for 16-byte loads
 
 // Per-facet constants in HBM, all SoA over facets (row r of an array with R rows: ptr[r * nF + f]).
@@ -94,9 +95,22 @@ struct vh_handle {
     double mu = 0.0, dt = 0.0;
     bool begun = false;
     int64_t count = 0;         // snapshots accumulated
+    bool sums_pending_zero = false;  // vh_begin happened, nothing accumulated yet: the next K3 overwrites the sums
     bool count_on_device = false;  // after an all-reduce the global count sits behind the sums until someone asks
     bool have_tau_last = false;
-    double* d_sums = nullptr;      // [15][nF] + 1 (snapshot count, filled for the all-reduce)
+    double* d_sums = nullptr;      // [15][nF] + 1 (snapshot count, filled for the all-reduce); one half of d_sums_block
+    // Peer-visible block (CUDA IPC over NVLink, vh_peer_*): two halves of sum_stride doubles used by alternate time
+    // loops, then VH_MAX_PEERS arrival counters.  Double buffering makes one cross-GPU barrier per reduction enough:
+    // a rank can only overwrite a half two loops later, after every peer has signalled the loop in between, which
+    // each peer does (stream order) after it finished reading that half.
+    double* d_sums_block = nullptr;
+    int64_t sum_stride = 0;
+    int loop_parity = 0;
+    double* d_sums_red = nullptr;  // [15][nF] + 1 globally reduced sums (local), written by the fused peer reduction
+    bool sums_reduced = false;     // vh_get_sums reads d_sums_red
+    bool peer_ready = false;
+    uint64_t peer_epoch = 0;
+    double* peer_block[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double* d_tau_last[2] = {nullptr, nullptr};  // [9][nF], ping-pong (read by first chunk, written by last)
     int tau_cur = 0;
     double* d_out5 = nullptr;      // [5][3*nF] TAWSS, OSI, RRT, ECAP, TWSSG
@@ -144,6 +158,14 @@ int k1_launch(vh_handle* h, const double* d_u, int64_t ncol, int64_t stride_elem
 // d_wss (may be null): [n_snap][nF][9].
 int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_elems, int prev_mode, double* d_wss);
 int k4_finalize(vh_handle* h, int64_t n_total, double* d_out5);  // d_out5: 5 arrays [nF*3] TAWSS,OSI,RRT,ECAP,TWSSG
+// Fused cross-GPU reduction + final formulas: waits until every rank has signalled `epoch`, adds the partial sums of
+// all ranks in rank order straight from their memory (NVLink peer loads), writes the reduced sums and the indices.
+struct PeerBlocks {
+    const double* block[VH_MAX_PEERS];
+};
+int k4_peer_signal(vh_handle* h, const PeerBlocks& pb, int64_t flags_off, uint64_t epoch);
+int k4_peer_reduce_finalize(vh_handle* h, const PeerBlocks& pb, int64_t half_off, int64_t flags_off, uint64_t epoch,
+                            int64_t n_total, double* d_red, double* d_out5);
 int k_free_run_buffers(vh_handle* h);
 
 FacetTables vh_tables(const vh_handle* h);

@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS, (ORDER == 2 || MULTI) ? 3 : 4) 
 // multi-facet launches have their own segment counts and partial-sum blocks
 __global__ void k3_fold(double* __restrict__ sums, const double* __restrict__ part_s, int gy_s,
                         const double* __restrict__ part_m, int gy_m, const int32_t* __restrict__ work, int64_t n_work,
-                        int64_t multi_start, int64_t nF) {
+                        int64_t multi_start, int64_t nF, int overwrite) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= VH_NSUM * n_work) return;
     const int64_t w = idx % n_work, i = idx / n_work;
@@ -396,7 +396,7 @@ __global__ void k3_fold(double* __restrict__ sums, const double* __restrict__ pa
     const bool multi = w >= multi_start;
     const double* p = (multi ? part_m : part_s) + i * n_work + w;
     const int gq = multi ? gy_m : gy_s;
-    double t = sums[i * nF + f];
+    double t = overwrite ? 0.0 : sums[i * nF + f];  // first launch of a time loop: no memset needed
     for (int q = 0; q < gq; ++q) t += p[(int64_t)q * VH_NSUM * n_work];
     sums[i * nF + f] = t;
 }
@@ -423,7 +423,103 @@ __global__ void k4_indices(const double* __restrict__ sums, int64_t nF, double c
     twssg[q] = sums[(int64_t)(12 + j) * nF + f] / count;
 }
 
+// ---- peer-memory reduction (one process per GPU, memory mapped with CUDA IPC) ------------------------------------------
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_peer(const double* p) {
+    // system-scope relaxed load: goes to the owner's memory (peer lines are never in the local L2, and the local L1
+    // holds nothing of them at this point of a fresh kernel), and -- unlike volatile -- loads may overlap
+    double v;
+    asm("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+// thread q tells rank q "rank `rank` has finished epoch `epoch`": everything this GPU wrote before (K3's sums) is
+// made visible system-wide first
+__global__ void k_peer_signal(PeerBlocks pb, int world, int rank, int64_t flags_off, uint64_t epoch, double* count_slot,
+                              double count) {
+    if (threadIdx.x == 0) *count_slot = count;  // the snapshot count rides behind the sums
+    __syncthreads();
+    if ((int)threadIdx.x >= world) return;
+    __threadfence_system();
+    uint64_t* flags = reinterpret_cast<uint64_t*>(const_cast<double*>(pb.block[threadIdx.x]) + flags_off);
+    st_release_sys(flags + rank, epoch);
+}
+
+// compute_hemodynamics.py:326-346 on sums that are still spread over the GPUs of the node
+__global__ void k4_peer_indices(PeerBlocks pb, int world, int rank, int64_t half_off, int64_t flags_off, uint64_t epoch,
+                                int64_t nF, double count, double* __restrict__ red, double* __restrict__ tawss,
+                                double* __restrict__ osi, double* __restrict__ rrt, double* __restrict__ ecap,
+                                double* __restrict__ twssg) {
+    if ((int)threadIdx.x < world) {
+        const uint64_t* flags = reinterpret_cast<const uint64_t*>(pb.block[rank] + flags_off);  // local memory
+        while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
+        }
+    }
+    __syncthreads();
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {  // snapshot count
+        double t = 0.0;
+        for (int q = 0; q < world; ++q) t += ld_peer(pb.block[q] + half_off + VH_NSUM * nF);
+        red[VH_NSUM * nF] = t;
+    }
+    if (i >= 3 * nF) return;
+    const int64_t f = i % nF;
+    const int j = (int)(i / nF);
+    const int rows[5] = {3 * j, 3 * j + 1, 3 * j + 2, 9 + j, 12 + j};
+    double pv[VH_MAX_PEERS][5];  // all peer loads in flight together (NVLink round trip ~ 1-2 us)
+#pragma unroll
+    for (int q = 0; q < VH_MAX_PEERS; ++q)
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+            pv[q][r] = q < world ? ld_peer(pb.block[q] + half_off + (int64_t)rows[r] * nF + f) : 0.0;
+    double v[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < VH_MAX_PEERS; ++q)
+            if (q < world) t += pv[q][r];  // rank order: bitwise identical on every rank
+        v[r] = t;
+        red[(int64_t)rows[r] * nF + f] = t;
+    }
+    const double mean_mag = norm3(v[0] / count, v[1] / count, v[2] / count);
+    const double ta = v[3] / count;
+    const double o = 0.5 * (1.0 - mean_mag / ta);
+    const int64_t q = 3 * f + j;
+    tawss[q] = ta;
+    osi[q] = o;
+    rrt[q] = 1.0 / mean_mag;
+    ecap[q] = o / ta;
+    twssg[q] = v[4] / count;
+}
+
 }  // namespace
+
+int k4_peer_signal(vh_handle* h, const PeerBlocks& pb, int64_t flags_off, uint64_t epoch) {
+    k_peer_signal<<<1, 32, 0, h->s_compute>>>(pb, h->world, h->rank, flags_off, epoch, h->d_sums + VH_NSUM * h->nF,
+                                              (double)h->count);
+    VH_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return VH_OK;
+}
+
+int k4_peer_reduce_finalize(vh_handle* h, const PeerBlocks& pb, int64_t half_off, int64_t flags_off, uint64_t epoch,
+                            int64_t n_total, double* d_red, double* d_out5) {
+    const int64_t nF = h->nF, n3 = 3 * nF;
+    k4_peer_indices<<<(unsigned)((n3 + 255) / 256), 256, 0, h->s_compute>>>(
+        pb, h->world, h->rank, half_off, flags_off, epoch, nF, (double)n_total, d_red, d_out5, d_out5 + n3,
+        d_out5 + 2 * n3, d_out5 + 3 * n3, d_out5 + 4 * n3);
+    VH_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return VH_OK;
+}
 
 FacetTables vh_tables(const vh_handle* h) {
     FacetTables T;
@@ -440,7 +536,10 @@ FacetTables vh_tables(const vh_handle* h) {
 }
 
 int k_free_run_buffers(vh_handle* h) {
-    if (h->d_sums) cudaFree(h->d_sums);
+    if (h->d_sums_block) cudaFree(h->d_sums_block);
+    if (h->d_sums_red) cudaFree(h->d_sums_red);
+    h->d_sums_block = h->d_sums_red = nullptr;
+    h->peer_ready = false;  // peers must map the new block again (vh_peer_init)
     if (h->d_tau_last[0]) cudaFree(h->d_tau_last[0]);
     if (h->d_tau_last[1]) cudaFree(h->d_tau_last[1]);
     if (h->d_part) cudaFree(h->d_part);
@@ -596,7 +695,9 @@ int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_el
         }
         const int64_t n = VH_NSUM * h->n_work;
         k3_fold<<<(unsigned)((n + 255) / 256), 256, 0, h->s_compute>>>(h->d_sums, part_s, gx_single ? ps.gy : 0, part_m,
-                                                                       pm.gy, h->d_work, h->n_work, h->multi_start, nF);
+                                                                       pm.gy, h->d_work, h->n_work, h->multi_start, nF,
+                                                                       h->sums_pending_zero ? 1 : 0);
+        h->sums_pending_zero = false;
         VH_CUDA(cudaGetLastError());
         h->launches += 1;
         pos += nb;

@@ -264,3 +264,17 @@ class HemoEngine:
 
     def barrier(self) -> None:
         check(self._lib.vh_nccl_barrier(self._h))
+
+    def peer_init(self) -> None:
+        """Map every rank's running sums over NVLink (CUDA IPC); collective, after ``nccl_init``."""
+        check(self._lib.vh_peer_init(self._h))
+
+    def peer_reduce_finalize(self, n_total: int, host: bool = True) -> Optional[Dict[str, np.ndarray]]:
+        """Fused cross-GPU reduction + final formulas (one kernel per rank, peer loads over NVLink)."""
+        if not host:
+            check(self._lib.vh_peer_reduce_finalize(self._h, int(n_total), None, None, None, None, None))
+            return None
+        out = {k: np.empty((self.nF, 3)) for k in ("TAWSS", "OSI", "RRT", "ECAP", "TWSSG")}
+        check(self._lib.vh_peer_reduce_finalize(self._h, int(n_total), _ptr(out["TAWSS"]), _ptr(out["OSI"]),
+                                                _ptr(out["RRT"]), _ptr(out["ECAP"]), _ptr(out["TWSSG"])))
+        return out

@@ -147,19 +147,38 @@ def cleanup_unique_id(world: int, directory: Optional[str] = None) -> None:
 
 
 class NcclComm:
-    """Device-side reduction through the engine's own NCCL communicator (the product path)."""
+    """Device-side reduction (the product path): NCCL for the plumbing, and -- when the ranks share an NVSwitch node
+    and can map each other's memory -- the fused peer-memory reduction + final formulas."""
 
-    def __init__(self, engine, rank: int, world: int):
-        from .engine import HemoEngine
+    def __init__(self, engine, rank: int, world: int, peer: bool = True):
+        from .engine import HemoEngine, VaspHemoError
         self.engine, self.rank, self.world = engine, rank, world
         uid = exchange_unique_id(rank, world, HemoEngine.nccl_unique_id)
         engine.nccl_init(uid, rank, world)
         engine.barrier()
         if rank == 0:
             cleanup_unique_id(world)
+        self.fused = False
+        if peer and world <= 8 and os.environ.get("VASP_B200_PEER_REDUCE", "1") != "0":
+            try:
+                engine.peer_init()   # collective: fails on every rank or on none
+                self.fused = True
+            except VaspHemoError as e:
+                if rank == 0:
+                    print(f"--- peer-memory reduction unavailable ({e}); using ncclAllReduce")
 
     def allreduce_sums(self) -> None:
         self.engine.allreduce_sums()
+
+    def reduce_finalize(self, n_total: int, host: bool = True):
+        """Global TAWSS/OSI/RRT/ECAP/TWSSG on every rank: fused peer reduction if mapped, else all-reduce + K4."""
+        if self.fused:
+            return self.engine.peer_reduce_finalize(n_total, host=host)
+        self.engine.allreduce_sums()
+        if host:
+            return self.engine.finalize(n_total)
+        self.engine.finalize_async(n_total)
+        return None
 
     def max(self, value: float) -> float:
         return self.engine.allreduce_max(value)
