@@ -38,6 +38,9 @@ WORKLOADS = {
     # offset-stenosis tutorial size: ~14 k fluid tets, P1 velocity, 1000 snapshots
     "stenosis_p1": dict(n=8, m=36, stenosis=0.45, bulge=0.0, order=1, snapshots=1000,
                         desc="offset-stenosis tutorial-size cylinder (13.8k tets), P1 velocity, 1000 snapshots"),
+    # same mesh with P2 velocity (the reference-native order, save_deg = 2): the small P2 profiling case
+    "stenosis_p2": dict(n=8, m=36, stenosis=0.45, bulge=0.0, order=2, snapshots=1000,
+                        desc="offset-stenosis tutorial-size cylinder (13.8k tets), P2 velocity, 1000 snapshots"),
     "aneurysm_p1": dict(n=40, m=208, stenosis=0.0, bulge=0.6, order=1, snapshots=2000,
                         desc="aneurysm-style fluid mesh (~2M tets), P1 velocity, 2000 snapshots"),
     "avf_p2": dict(n=52, m=308, stenosis=0.2, bulge=0.0, order=2, snapshots=4000,

@@ -290,6 +290,14 @@ __global__ void __launch_bounds__(32 * K2_WARPS, (ORDER == 2 || MULTI) ? 3 : 4) 
         for (int b = 0; b < 4; ++b) gam[b] = g[b][0] * n[0] + g[b][1] * n[1] + g[b][2] * n[2];
     }
 
+    // tau_prev of the block's first column is external (zero, or carried over from the last launch): lane i holds
+    // component i.  It is fetched here and handed to lane 0 by shuffle in the first pass -- a (predicated) load inside
+    // the pass loop shares a scoreboard with the prefetch loads and makes every pass wait for its own prefetch
+    // (ncu r1i: 41 % of all stall samples on the first shuffle after the prefetch).
+    const bool seeded = seg0 == 0;
+    double prev_seed = 0.0;
+    if (seeded && a.prev_mode == 1 && lane < NT) prev_seed = a.tau_last_in[(int64_t)lane * nF + f];
+
     double acc[VH_NSUM];
 #pragma unroll
     for (int i = 0; i < VH_NSUM; ++i) acc[i] = 0.0;
@@ -326,9 +334,12 @@ __global__ void __launch_bounds__(32 * K2_WARPS, (ORDER == 2 || MULTI) ? 3 : 4) 
             tau_dense<ORDER>(M, v, a.mu, tau);
         else
             tau_single<ORDER>(g, n, gam, v, a.mu, tau);
-        if (col < 0) {  // no column before the block's first: tau_prev is zero or carried over from the last launch
+        if (j == 0 && seeded) {  // warp-uniform; lane 0 sits on the column before the block's first (col < 0)
 #pragma unroll
-            for (int i = 0; i < NT; ++i) tau[i] = a.prev_mode == 1 ? a.tau_last_in[(int64_t)i * nF + f] : 0.0;
+            for (int i = 0; i < NT; ++i) {
+                const double t = __shfl_sync(0xffffffffu, prev_seed, i);
+                if (lane == 0) tau[i] = t;
+            }
         }
         double dw[9];
 #pragma unroll
