@@ -87,7 +87,8 @@ struct vh_handle {
     // wall-layer nodes = velocity nodes referenced by any wall cell, ascending in vector position
     int64_t nWn = 0, nWn_pad = 0;      // padded to a multiple of 32 (padding repeats the last node)
     int32_t* d_wall_slot = nullptr;    // [nWn_pad] element offset of the node inside a snapshot vector
-    // K1 output: W[(3 * wall node + component) * w_ld + column], columns = snapshots of the current launch
+    // K1 output: W[((wall node * (w_ld / 32) + column / 32) * 3 + component) * 32 + column % 32], columns = snapshots
+    // of the current launch (time tiles of 32, 768 contiguous bytes per node and tile)
     double* d_W = nullptr;
     int64_t w_ld = 0;                  // columns allocated per row (multiple of 32)
 
@@ -149,7 +150,8 @@ int k0_build_velocity_map(vh_handle* h, int order, const double* refined_xyz, in
                           const int64_t* node_perm);
 
 // ---- K1 (k1_stage.cu) ------------------------------------------------------------------------------------------------
-// W[(3 i + c) * ld + col] = u[col * stride_elems + comp_offset[c] + wall_slot[i]] for col < ncol, i < nWn_pad
+// W[((i * (w_ld / 32) + col / 32) * 3 + c) * 32 + col % 32] = u[col * stride_elems + comp_offset[c] + wall_slot[i]]
+// for col < ncol, i < nWn_pad (zero up to the next multiple of 32 columns)
 int k1_launch(vh_handle* h, const double* d_u, int64_t ncol, int64_t stride_elems);
 
 // ---- K2/K3/K4 (k2_wall.cu) ---------------------------------------------------------------------------------------

@@ -5,14 +5,16 @@
 // traction (:113-115 integrates over ds only).  K1 is that transfer restricted to the wall layer, applied to a
 // whole block of snapshots at once and written transposed:
 //
-//     W[(3 i + c) * ld + col] = u[col * stride + comp_offset[c] + wall_slot[i]]      i < nWn_pad, col < ncol
+//     W[((i * ntile + col / 32) * 3 + c) * 32 + col % 32] = u[col * stride + comp_offset[c] + wall_slot[i]]
+//                                                                                  i < nWn_pad, col < 32 * ceil(ncol / 32)
 //
-// so that K2 can give one facet to a warp and consecutive snapshots to its lanes: every K2 load is then 32
-// consecutive doubles (256 B, 8 full sectors, 2 L1 wavefronts) instead of 32 scattered 8-byte gathers.
+// (columns past ncol are zero) so that K2 can give one facet to a warp and the 32 snapshots of a time tile to its
+// lanes: every K2 load is then 32 consecutive, 256-byte-aligned doubles (8 full sectors, 2 L1 wavefronts) instead of
+// 32 scattered 8-byte gathers, and the three components of a node sit 256 bytes apart (immediate offsets).
 //
 // Tile = 32 wall nodes x 32 snapshots x 3 components through shared memory.  Reads run along the node list, which
 // K0 sorted by position in the vector: as coalesced as the mesh numbering allows, and each wall node is read from
-// HBM once per snapshot (not once per facet that touches it).  Writes run along time: 256 B per (node, component).
+// HBM once per snapshot (not once per facet that touches it).  Writes: 768 contiguous bytes per (node, time tile).
 #include "common.cuh"
 
 namespace {
@@ -29,7 +31,7 @@ __device__ __forceinline__ double ld_stream(const double* p) {
 
 __global__ void __launch_bounds__(TILE* ROWS)
     k1_stage(const double* __restrict__ u, int64_t stride, int ncol, const int32_t* __restrict__ wall_slot,
-             int64_t off0, int64_t off1, int64_t off2, double* __restrict__ W, int64_t ld) {
+             int64_t off0, int64_t off1, int64_t off2, double* __restrict__ W, int64_t ntile) {
     __shared__ double tile[3][TILE][TILE + 1];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int64_t node0 = (int64_t)blockIdx.x * TILE;
@@ -59,10 +61,10 @@ __global__ void __launch_bounds__(TILE* ROWS)
 #pragma unroll
     for (int r = 0; r < TILE / ROWS; ++r) {
         const int64_t node = node0 + ty + ROWS * r;
-        double* q = W + (3 * node) * ld + col0 + tx;
+        double* q = W + ((node * ntile + blockIdx.y) * 3) * TILE + tx;
         q[0] = tile[0][tx][ty + ROWS * r];
-        q[ld] = tile[1][tx][ty + ROWS * r];
-        q[2 * ld] = tile[2][tx][ty + ROWS * r];
+        q[TILE] = tile[1][tx][ty + ROWS * r];
+        q[2 * TILE] = tile[2][tx][ty + ROWS * r];
     }
 }
 
@@ -75,7 +77,7 @@ int k1_launch(vh_handle* h, const double* d_u, int64_t ncol, int64_t stride_elem
     VH_CHECK(gy <= 65535, VH_ERR_ARG, "k1_launch: too many snapshots in one block");
     dim3 grid((unsigned)(h->nWn_pad / TILE), (unsigned)gy), block(TILE, ROWS);
     k1_stage<<<grid, block, 0, h->s_compute>>>(d_u, stride_elems, (int)ncol, h->d_wall_slot, h->comp_offset[0],
-                                               h->comp_offset[1], h->comp_offset[2], h->d_W, h->w_ld);
+                                               h->comp_offset[1], h->comp_offset[2], h->d_W, h->w_ld / TILE);
     VH_CUDA(cudaGetLastError());
     h->launches += 1;
     return VH_OK;

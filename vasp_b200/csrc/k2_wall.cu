@@ -10,32 +10,32 @@
 //   TWSSG += project_dg(|dtau/dt|)       (:309-312) 7-point degree-5 rule, closed-form P1 mass inverse
 // and the final formulas (:326-346).
 //
-// Work decomposition: one WARP per (facet, time segment); the 32 LANES are 32 consecutive snapshots.  With the
-// time-major block W that K1 wrote, every load of a cell dof is 32 consecutive doubles (256 B): full sectors, two L1
-// wavefronts.  Facet geometry is warp-uniform (broadcast loads), facets of multi-facet cells get their own launch
-// (no divergence), tau of the previous snapshot comes from the neighbouring lane (shuffle) and each lane keeps its
-// share of the 15 running sums in registers until one fixed-order butterfly at the end.  Lane 0 of every lane pass
-// recomputes the column before the pass instead of communicating with the previous pass or segment (TWSSG's
-// one-step dependence), so a pass advances 31 snapshots.  The rows of the next pass are in flight while the
-// current one is computed: cp.async into a per-warp shared-memory ring for P2 (30 rows; every lane copies and later
-// reads only its own column, so no barrier), a register double buffer for P1 (12 rows).  Partial sums of the
-// segments go to `part` and are folded into the running sums by k3_fold in fixed order: results are bitwise
-// reproducible for a given launch shape.  (A TMA variant -- one cp.async.bulk of 288 B per row and pass, mbarrier
-// completion -- was measured 10-20 % slower than cp.async.ca: the copies bypass L1, where neighbouring facets share
-// rows, and are too small to amortise; see DESIGN.md.)
+// Work decomposition: one WARP per (facet, time segment); the 32 LANES are the 32 snapshots of one time TILE of the
+// staged block W that K1 wrote (W[node][tile][component][32], 768 contiguous bytes per node and tile).  Every load of
+// a cell dof is 32 consecutive, 256-byte-aligned doubles; the three components sit at immediate offsets.  The rows of
+// a tile land in a per-warp shared-memory buffer by cp.async (each lane copies and later reads only its own column,
+// so no barrier): two stages for P1 (the next tile is in flight while this one is computed), one stage refilled as
+// soon as its last read is done for P2 (its 7.5 KB per warp would otherwise halve the occupancy).  Per-facet constants
+// live in shared memory too (warp-uniform broadcast reads): for P1 data in a cell with one exterior facet the whole
+// traction is a 3 x 12 operator built in the prologue; for P2 the 19 geometry numbers of the closed form.  That keeps
+// the kernels at 64 (P1) / ~100 (P2) registers, i.e. 32 / 20 warps per SM: the ncu captures of the previous version
+// (profiles/r1k_*) showed a latency-bound kernel -- fixed-latency fp64 dependency stalls with 3-4 warps per scheduler
+// -- not a bandwidth-bound one.
+//
+// TWSSG's one-step dependence: inside a tile tau of the previous snapshot comes from the neighbouring lane (shuffle),
+// across tiles lane 0 keeps the last lane's tau of the previous pass, and across SEGMENTS nothing is communicated:
+// each segment records tau of its first and last column and k3_fold adds the missing boundary terms
+// P(|tau_first(s) - tau_last(s-1)| / dt) when it folds the segments' partial sums -- in fixed order, so results are
+// bitwise reproducible for a given launch shape.  Facets of multi-facet cells get their own launch (no divergence).
 //
 // Local vertex labels are facet-canonical (K0): 0,1,2 = the facet's vertices in boundary-cell order, 3 = the
 // opposite vertex; P2 edge dofs 4..9 = e01,e02,e12,e03,e13,e23.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace {
-
-template <int ORDER>
-struct Dofs {
-    static constexpr int N = ORDER == 2 ? 10 : 4;
-};
 
 __host__ __device__ constexpr int edge_dof(int a, int b) {
     // canonical edge order e01,e02,e12,e03,e13,e23 -> 4..9
@@ -51,84 +51,144 @@ constexpr double Q_A = 0.10128650732345633, Q_B = 0.79742698535308720;
 constexpr double Q_C = 0.47014206410511505, Q_D = 0.05971587178976981;
 constexpr double Q_W0 = 0.225, Q_W1 = 0.12593918054482717, Q_W2 = 0.13239415278850616;
 
-struct Vel {
-    // velocity of the cell dofs, one snapshot
-    double x[10], y[10], z[10];
+constexpr int K2_WARPS = 4;
+
+// Compile-time shape of one code path (ORDER x single-/multi-facet cell).  How the dof values reach the arithmetic:
+//   P1  DIRECT: ld.global.nc straight into registers (12 doubles), the next tile's loads issued before this tile's
+//       arithmetic (register double buffer)
+//   P2  ring:   cp.async into a per-warp shared-memory landing buffer of two tiles (each lane copies and later reads
+//       only its own column: no barrier); 30 doubles per lane would not fit twice in registers
+// Per-facet constants (grad lambda (12), n (3), gamma (4)) stay in registers.  Alternatives that were measured and
+// dropped: constants or a 3 x 12 traction operator in shared memory to reach 32 warps per SM --
+// every warp-uniform LDS still costs its data-path cycles, the kernel became MIO-bound; a single-stage landing buffer
+// with 20 warps per SM (spills); L1 prefetch two tiles ahead (no effect: W is L2-resident after K1).
+// Shared memory per warp, in doubles: [STAGES][3 N][32] landing buffer | [CARRY] tau of the last lane of the previous
+// pass (touched by lane 0 only).
+template <int ORDER, bool MULTI>
+struct K2Cfg {
+    static constexpr int N = ORDER == 2 ? 10 : 4;
+    // P1 data in a cell with one exterior facet: tau is the same at the three facet vertices, so one magnitude and
+    // P(|w|) = |w| exactly (the projection reproduces constants)
+    static constexpr bool FLAT = ORDER == 1 && !MULTI;
+    static constexpr int NT = FLAT ? 3 : 9;
+    static constexpr bool DIRECT = ORDER == 1;
+    static constexpr bool PREF = DIRECT;
+    static constexpr int STAGES = DIRECT ? 0 : 2;
+    static constexpr int STAGE_DOUBLES = 3 * N * 32;
+    static constexpr int CARRY = FLAT ? 0 : 10;
+    static constexpr int WARP_DOUBLES = STAGES * STAGE_DOUBLES + CARRY;
+};
+template <int ORDER>
+struct K2Launch {
+    static constexpr int WARP_DOUBLES = K2Cfg<ORDER, true>::WARP_DOUBLES > K2Cfg<ORDER, false>::WARP_DOUBLES
+                                            ? K2Cfg<ORDER, true>::WARP_DOUBLES
+                                            : K2Cfg<ORDER, false>::WARP_DOUBLES;
+    static constexpr int SMEM_BYTES = K2_WARPS * WARP_DOUBLES * (int)sizeof(double);
+    static constexpr int MIN_BLOCKS = ORDER == 1 ? 4 : 3;  // 128 | 168 registers
 };
 
-// Tangential traction Ft = F - (F.n) n, F = -mu (grad u + grad u^T) n, at local vertices listed in VS..., for the
-// face with unit normal n.  g[a] = grad lambda_a.
-//   P2: grad u (v_a) = H + 4 (u_a (x) g_a + sum_{b != a} u_ab (x) g_b),  H = -sum_b u_b (x) g_b
-//   P1: grad u       = -H  (constant)
-// Only G n and G^T n are formed:  G n = sum_nodes u_node (grad phi_node . n),  G^T n = sum grad phi_node (u_node . n).
-template <int ORDER, int V>
-__device__ __forceinline__ void ft_vertex(const double (&g)[4][3], const double (&n)[3], const double (&gam)[4],
-                                          const Vel& v, const double (&un)[10], const double (&c)[3], double mu,
-                                          double (&ft)[3]) {
-    double s[3];
-    if (ORDER == 2) {
-        double ex = v.x[V] * gam[V], ey = v.y[V] * gam[V], ez = v.z[V] * gam[V];
-        double tx = g[V][0] * un[V], ty = g[V][1] * un[V], tz = g[V][2] * un[V];
+// sqrt(x) for x >= 0 without the library's special-case branch: rsqrt seed (MUFU.RSQ64H, ~2^-22), two coupled
+// Newton steps on g ~ sqrt(x), h ~ 1 / (2 sqrt(x)) -> error of a few ulp.  Zero and anything below 2^-1020 give 0.
+// Branch-free, so that the independent norms of a pass (two for P1, ten for P2) interleave instead of forming one
+// serial chain of ten dependent fp64 operations each.
+__device__ __forceinline__ double sqrt_nb(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    if (__double2hiint(x) < 0x00300000) y = 0.0;
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    return fma(g, r, g);
+}
+
+__device__ __forceinline__ double norm3(double a, double b, double c) { return sqrt_nb(fma(a, a, fma(b, b, c * c))); }
+
+// Tangential traction Ft = F - (F.n) n, F = -mu (grad u + grad u^T) n, of P1 data (grad u constant in the cell):
+// G n = sum_b u_b (grad lambda_b . n),  G^T n = sum_b grad lambda_b (u_b . n).  G(i) = {g[4][3], n[3], gam[4]}[i],
+// U(3 b + d) = component d of the velocity at vertex b.
+template <class GF, class UF>
+__device__ __forceinline__ void tau_p1(GF G, UF U, double mu, double (&ft)[3]) {
+    const double n0 = G(12), n1 = G(13), n2 = G(14);
+    double s[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const double un = fma(U(3 * b + 2), n2, fma(U(3 * b + 1), n1, U(3 * b) * n0));
+#pragma unroll
+        for (int d = 0; d < 3; ++d) s[d] = fma(U(3 * b + d), G(15 + b), fma(G(3 * b + d), un, s[d]));
+    }
+    const double fx = -mu * s[0], fy = -mu * s[1], fz = -mu * s[2];
+    const double fn = fx * n0 + fy * n1 + fz * n2;
+    ft[0] = fma(-fn, n0, fx);
+    ft[1] = fma(-fn, n1, fy);
+    ft[2] = fma(-fn, n2, fz);
+}
+
+// P2 data, cell with one exterior facet: tau[3 V + d] at the facet vertices V = 0, 1, 2.
+//   grad u (v_a) = H + 4 (u_a (x) g_a + sum_{b != a} u_ab (x) g_b),  H = -sum_b u_b (x) g_b
+// Only G n and G^T n are formed.  The constants G(i) and the dof values U(3 k + d) are fetched where they are needed
+// (from registers or shared memory), so that little more than the ten u_k . n stays live.
+template <class GF, class UF>
+__device__ __forceinline__ void tau_p2(GF G, UF U, double mu, double (&tau)[9]) {
+    const double n0 = G(12), n1 = G(13), n2 = G(14);
+    double un[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) un[k] = fma(U(3 * k + 2), n2, fma(U(3 * k + 1), n1, U(3 * k) * n0));
+    double c[3] = {0.0, 0.0, 0.0};  // (H + H^T) n
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) c[d] = fma(-U(3 * b + d), G(15 + b), fma(-G(3 * b + d), un[b], c[d]));
+    }
+#pragma unroll
+    for (int V = 0; V < 3; ++V) {
+        double e[3], t[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            e[d] = U(3 * V + d) * G(15 + V);
+            t[d] = G(3 * V + d) * un[V];
+        }
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             if (b == V) continue;
-            const int e = edge_dof(V, b);
-            ex = fma(v.x[e], gam[b], ex);
-            ey = fma(v.y[e], gam[b], ey);
-            ez = fma(v.z[e], gam[b], ez);
-            tx = fma(g[b][0], un[e], tx);
-            ty = fma(g[b][1], un[e], ty);
-            tz = fma(g[b][2], un[e], tz);
+            const int k = edge_dof(V, b);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                e[d] = fma(U(3 * k + d), G(15 + b), e[d]);
+                t[d] = fma(G(3 * b + d), un[k], t[d]);
+            }
         }
-        s[0] = fma(4.0, ex + tx, c[0]);
-        s[1] = fma(4.0, ey + ty, c[1]);
-        s[2] = fma(4.0, ez + tz, c[2]);
-    } else {
-        s[0] = -c[0];
-        s[1] = -c[1];
-        s[2] = -c[2];
+        const double fx = -mu * fma(4.0, e[0] + t[0], c[0]);
+        const double fy = -mu * fma(4.0, e[1] + t[1], c[1]);
+        const double fz = -mu * fma(4.0, e[2] + t[2], c[2]);
+        const double fn = fx * n0 + fy * n1 + fz * n2;
+        tau[3 * V + 0] = fma(-fn, n0, fx);
+        tau[3 * V + 1] = fma(-fn, n1, fy);
+        tau[3 * V + 2] = fma(-fn, n2, fz);
     }
-    double fx = -mu * s[0], fy = -mu * s[1], fz = -mu * s[2];
-    double fn = fx * n[0] + fy * n[1] + fz * n[2];
-    ft[0] = fma(-fn, n[0], fx);
-    ft[1] = fma(-fn, n[1], fy);
-    ft[2] = fma(-fn, n[2], fz);
 }
 
-// common part c = H n + H^T n and un = u_node . n
-template <int ORDER>
-__device__ __forceinline__ void face_common(const double (&g)[4][3], const double (&n)[3], const double (&gam)[4],
-                                            const Vel& v, double (&un)[10], double (&c)[3]) {
+// tau of a facet whose cell owns several exterior facets: dense operator from K0 (SurfaceProjector's block solve
+// folded with the contributing faces), warp-uniform coefficient loads
+template <int N, class UF>
+__device__ __forceinline__ void tau_dense(const double* __restrict__ M, UF U, double mu, double (&tau)[9]) {
 #pragma unroll
-    for (int k = 0; k < Dofs<ORDER>::N; ++k) un[k] = fma(v.z[k], n[2], fma(v.y[k], n[1], v.x[k] * n[0]));
-    c[0] = c[1] = c[2] = 0.0;
+    for (int i = 0; i < 9; ++i) tau[i] = 0.0;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        c[0] = fma(-v.x[b], gam[b], fma(-g[b][0], un[b], c[0]));
-        c[1] = fma(-v.y[b], gam[b], fma(-g[b][1], un[b], c[1]));
-        c[2] = fma(-v.z[b], gam[b], fma(-g[b][2], un[b], c[2]));
+    for (int q = 0; q < 3 * N; ++q) {
+        const double val = U(q);
+        const double2* row = reinterpret_cast<const double2*>(M + q * VH_MROW);
+#pragma unroll
+        for (int h2 = 0; h2 < 5; ++h2) {
+            const double2 m2 = __ldg(row + h2);
+            tau[2 * h2] = fma(m2.x, val, tau[2 * h2]);
+            if (h2 < 4) tau[2 * h2 + 1] = fma(m2.y, val, tau[2 * h2 + 1]);
+        }
     }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) tau[i] *= -mu;
 }
-
-// tau[3*j + c] for a facet whose cell owns no other exterior facet
-template <int ORDER>
-__device__ __forceinline__ void tau_single(const double (&g)[4][3], const double (&n)[3], const double (&gam)[4],
-                                           const Vel& v, double mu, double (&tau)[9]) {
-    double un[10], c[3], ft[3];
-    face_common<ORDER>(g, n, gam, v, un, c);
-    ft_vertex<ORDER, 0>(g, n, gam, v, un, c, mu, ft);
-    tau[0] = ft[0]; tau[1] = ft[1]; tau[2] = ft[2];
-    if (ORDER == 2) {
-        ft_vertex<ORDER, 1>(g, n, gam, v, un, c, mu, ft);
-        tau[3] = ft[0]; tau[4] = ft[1]; tau[5] = ft[2];
-        ft_vertex<ORDER, 2>(g, n, gam, v, un, c, mu, ft);
-        tau[6] = ft[0]; tau[7] = ft[1]; tau[8] = ft[2];
-    } else {
-        tau[3] = tau[6] = ft[0]; tau[4] = tau[7] = ft[1]; tau[5] = tau[8] = ft[2];
-    }
-}
-
-__device__ __forceinline__ double norm3(double a, double b, double c) { return sqrt(fma(a, a, fma(b, b, c * c))); }
 
 // P(|w|) on the boundary triangle: p_j = 12 s_j - 3 sum_i s_i,  s_i = sum_q wq phi_i(x_q) |w(x_q)|   (area cancels)
 __device__ __forceinline__ void twssg_project(const double (&w)[9], double (&p)[3]) {
@@ -152,25 +212,28 @@ __device__ __forceinline__ void twssg_project(const double (&w)[9], double (&p)[
     }
 }
 
-__device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
-
+// One launch covers both kinds of work items: blocks [0, gx_multi * gy_multi) take the facets of multi-facet cells
+// (the long-running ones, scheduled first), the rest the single-facet-cell facets.  Each kind has its own split of
+// the block's tiles into segments and its own partial-sum / boundary buffers.
+struct K2Seg {
+    int gx, gy;             // blocks along the work list, segments
+    int tile_base, tile_extra;  // segment y owns tile_base (+1 if y < tile_extra) consecutive tiles
+    double* part;           // [gy][15][n_work] partial sums of the segments
+    double* bnd;            // [gy][2][9][n_work] tau of every segment's first and last column
+};
 struct K2Args {
     FacetTables T;
-    const double* W;        // staged block (K1)
-    int64_t ld;
+    const double* W;        // staged block (K1): W[((node * ntile_ld + tile) * 3 + c) * 32 + column in tile]
+    int ntile_ld;           // tiles allocated per wall node
     int ncol;               // columns in the block
     int r0;                 // first real column (1 when column 0 is a halo snapshot that only seeds tau_prev)
-    int pass_base, pass_extra;  // segment y owns pass_base (+1 if y < pass_extra) lane passes of K2_COLS columns
     int prev_mode;          // tau_prev of the first real column when r0 == 0: 0 zero, 1 tau_last_in
+    K2Seg multi, single;
     const double* tau_last_in;
     double* tau_last_out;   // [9][nF]
-    double* part;           // [gridDim.y][15][n_work]
     double* wss_out;        // [ncol - r0][nF][9] or null
     double mu, inv_dt;
 };
-
-constexpr int K2_WARPS = 4;
-constexpr int K2_COLS = 31;  // real columns per lane pass; lane 0 recomputes the column before them
 
 __device__ __forceinline__ void cp_async8(uint32_t dst_smem, const double* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
@@ -181,235 +244,236 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// Shared-memory ring of the cp.async path: [warp][stage][3 * dof + c][lane]
-template <int ORDER>
-constexpr int k2_smem_bytes() {
-    return ORDER == 2 ? K2_WARPS * 2 * 3 * Dofs<ORDER>::N * 32 * (int)sizeof(double) : 0;
-}
-
-// tau of a facet whose cell owns several exterior facets: dense operator from K0, warp-uniform coefficient loads
-template <int ORDER>
-__device__ __forceinline__ void tau_dense(const double* __restrict__ M, const Vel& v, double mu, double (&tau)[9]) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) tau[i] = 0.0;
-#pragma unroll
-    for (int k = 0; k < Dofs<ORDER>::N; ++k) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const double val = c == 0 ? v.x[k] : c == 1 ? v.y[k] : v.z[k];
-            const double2* row = reinterpret_cast<const double2*>(M + (3 * k + c) * VH_MROW);
-#pragma unroll
-            for (int h2 = 0; h2 < 5; ++h2) {
-                const double2 m2 = __ldg(row + h2);
-                tau[2 * h2] = fma(m2.x, val, tau[2 * h2]);
-                if (h2 < 4) tau[2 * h2 + 1] = fma(m2.y, val, tau[2 * h2 + 1]);
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 9; ++i) tau[i] *= -mu;
-}
-
-// One warp = one facet x one time segment; the 32 lanes are 32 consecutive columns of the staged block.
+// One warp = one facet x one time segment; the 32 lanes are the 32 columns of a tile of the staged block.
 // MULTI = false: facets whose cell owns no other exterior facet (work[0, multi_start)); MULTI = true: the rest.
 template <int ORDER, bool MULTI>
-__global__ void __launch_bounds__(32 * K2_WARPS, (ORDER == 2 || MULTI) ? 3 : 4) k2_wall(const K2Args a) {
-    extern __shared__ __align__(16) double k2_smem[];
-    constexpr int N = Dofs<ORDER>::N;
-    constexpr bool RING = ORDER == 2;  // cp.async shared-memory ring (else: register double buffer)
+__device__ __forceinline__ void k2_body(const K2Args& a, const K2Seg& sg, int bx, int y, double* k2_smem) {
+    using C = K2Cfg<ORDER, MULTI>;
+    constexpr int N = C::N, NT = C::NT, NV = 3 * C::N;
+    constexpr bool FLAT = C::FLAT, DIRECT = C::DIRECT, PREF = C::PREF;
     const FacetTables& T = a.T;
     const int64_t nF = T.nF;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t wi = (int64_t)blockIdx.x * K2_WARPS + wib;
+    const int64_t wi = (int64_t)bx * K2_WARPS + wib;
     const int64_t w = MULTI ? wi + T.multi_start : wi;
     if (w >= (MULTI ? T.n_work : T.multi_start)) return;
     const int32_t f = T.work[w];
     if (f < 0) return;  // padding entry (warp-uniform)
-    // P1 data in a cell with one exterior facet: tau is the same at the three facet vertices, so one magnitude and
-    // P(|w|) = |w| exactly (the projection reproduces constants)
-    constexpr bool FLAT = (ORDER == 1) && !MULTI;
-    constexpr int NT = FLAT ? 3 : 9;
 
-    const int y = blockIdx.y;
-    const int pass0 = y * a.pass_base + min(y, a.pass_extra);
-    const int npass = a.pass_base + (y < a.pass_extra ? 1 : 0);
-    const int seg0 = a.r0 + pass0 * K2_COLS;  // first real column of this segment
-    const int seg1 = min(seg0 + npass * K2_COLS, a.ncol);
+    const int t0 = y * sg.tile_base + min(y, sg.tile_extra);
+    const int nt = sg.tile_base + (y < sg.tile_extra ? 1 : 0);
 
-    // x-component row of every cell dof (y, z follow at +ld, +2 ld), already offset to this lane's first column
-    const double* rp[N];
+    double* const ring = k2_smem + (size_t)wib * K2Launch<ORDER>::WARP_DOUBLES;
+    double* const carry_s = ring + C::STAGES * C::STAGE_DOUBLES;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring + lane);
+
+    // element offset inside W of (cell dof k, tile t0, component 0, this lane's column); W holds < 2^31 doubles
+    int32_t rb[N];
 #pragma unroll
-    for (int k = 0; k < N; ++k)
-        rp[k] = a.W + 3 * (int64_t)T.row[(int64_t)k * nF + f] * a.ld + (seg0 + lane - 1);
-    const int64_t ld = a.ld;
-    // column offset of pass j relative to rp: the lane's column is clamped into [0, seg1)
-    auto pass_off = [&](int j) {
-        const int col = seg0 + j * K2_COLS + lane - 1;
-        return min(max(col, 0), seg1 - 1) - (seg0 + lane - 1);
-    };
-
-    double* const ring = k2_smem + (size_t)wib * 2 * 3 * N * 32 + lane;
-    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
-    Vel vn;  // register double buffer (P1)
-    auto prefetch = [&](int j) {
-        const int off = pass_off(j);
-        if (RING) {
-            const uint32_t dst = ring_s + (uint32_t)((j & 1) * 3 * N * 32 * sizeof(double));
+    for (int k = 0; k < N; ++k) rb[k] = (T.row[(int64_t)k * nF + f] * a.ntile_ld + t0) * 96 + lane;
+    double v[DIRECT ? NV : 1], vn[PREF ? NV : 1];
+    auto fetch = [&](int j, int stage) {  // tile t0 + j -> landing stage | registers
+        if constexpr (DIRECT) {
 #pragma unroll
             for (int k = 0; k < N; ++k) {
-                const double* p = rp[k] + off;
-                cp_async8(dst + (3 * k + 0) * 256, p);
-                cp_async8(dst + (3 * k + 1) * 256, p + ld);
-                cp_async8(dst + (3 * k + 2) * 256, p + 2 * ld);
+                const double* p = a.W + (rb[k] + j * 96);
+#pragma unroll
+                for (int d = 0; d < 3; ++d) (PREF ? vn : v)[3 * k + d] = __ldg(p + 32 * d);
+            }
+        } else {
+            const uint32_t dst = ring_s + (uint32_t)(stage * C::STAGE_DOUBLES * sizeof(double));
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                const double* p = a.W + (rb[k] + j * 96);
+#pragma unroll
+                for (int d = 0; d < 3; ++d) cp_async8(dst + (3 * k + d) * 256, p + 32 * d);
             }
             cp_async_commit();
-        } else {
-#pragma unroll
-            for (int k = 0; k < N; ++k) {
-                const double* p = rp[k] + off;
-                vn.x[k] = __ldg(p);
-                vn.y[k] = __ldg(p + ld);
-                vn.z[k] = __ldg(p + 2 * ld);
-            }
         }
     };
-    prefetch(0);
+    if (PREF || !DIRECT) fetch(0, 0);
 
-    double g[4][3], n[3], gam[4];
+    // ---- per-facet constants: {grad lambda [4][3], n [3], gamma [4]} in registers, or the dense operator's address -----
     const double* M = nullptr;
-    if (MULTI) {
+    double gr[MULTI ? 1 : 19];
+    if constexpr (MULTI) {
         M = T.m_mat + (size_t)wi * 3 * N * VH_MROW;
     } else {
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
+        for (int i = 0; i < 12; ++i) gr[i] = T.glam[(int64_t)i * nF + f];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) g[b][d] = T.glam[(int64_t)(3 * b + d) * nF + f];
+        for (int d = 0; d < 3; ++d) gr[12 + d] = T.normal[(int64_t)d * nF + f];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) n[d] = T.normal[(int64_t)d * nF + f];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) gam[b] = g[b][0] * n[0] + g[b][1] * n[1] + g[b][2] * n[2];
+        for (int b = 0; b < 4; ++b) gr[15 + b] = gr[3 * b] * gr[12] + gr[3 * b + 1] * gr[13] + gr[3 * b + 2] * gr[14];
     }
-
-    // tau_prev of the block's first column is external (zero, or carried over from the last launch): lane i holds
-    // component i.  It is fetched here and handed to lane 0 by shuffle in the first pass -- a (predicated) load inside
-    // the pass loop shares a scoreboard with the prefetch loads and makes every pass wait for its own prefetch
-    // (ncu r1i: 41 % of all stall samples on the first shuffle after the prefetch).
-    const bool seeded = seg0 == 0;
-    double prev_seed = 0.0;
-    if (seeded && a.prev_mode == 1 && lane < NT) prev_seed = a.tau_last_in[(int64_t)lane * nF + f];
-
-    double acc[VH_NSUM];
+    // tau_prev of the segment's first column.  Segment 0: zero, or carried over from the last launch; later
+    // segments: unknown here -- lane 0 skips that one TWSSG term and k3_fold adds it from the boundary records.
+    double carry[FLAT ? 3 : 1];
+    if constexpr (FLAT) {
 #pragma unroll
-    for (int i = 0; i < VH_NSUM; ++i) acc[i] = 0.0;
+        for (int i = 0; i < 3; ++i)
+            carry[i] = (y == 0 && a.prev_mode == 1 && lane == 0) ? a.tau_last_in[(int64_t)i * nF + f] : 0.0;
+    } else if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) carry_s[i] = (y == 0 && a.prev_mode == 1) ? a.tau_last_in[(int64_t)i * nF + f] : 0.0;
+    }
+    __syncwarp();
 
-    for (int j = 0; j < npass; ++j) {
-        Vel v;
-        if (RING) {
-            if (j + 1 < npass) {
-                prefetch(j + 1);
+    constexpr int NACC = FLAT ? 5 : VH_NSUM;
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+
+    for (int j = 0; j < nt; ++j) {
+        const double* sv = ring + (j & 1) * C::STAGE_DOUBLES + lane;  // sv[(3 k + d) * 32]
+        if constexpr (DIRECT) {
+            if constexpr (PREF) {
+#pragma unroll
+                for (int q = 0; q < NV; ++q) v[q] = vn[q];
+                if (j + 1 < nt) fetch(j + 1, 0);
+            } else {
+                fetch(j, 0);
+            }
+        } else {
+            if (j + 1 < nt) {
+                fetch(j + 1, (j + 1) & 1);
                 cp_async_wait<1>();
             } else {
                 cp_async_wait<0>();
             }
-            const double* sv = ring + (j & 1) * 3 * N * 32;
-#pragma unroll
-            for (int k = 0; k < N; ++k) {
-                v.x[k] = sv[(3 * k + 0) * 32];
-                v.y[k] = sv[(3 * k + 1) * 32];
-                v.z[k] = sv[(3 * k + 2) * 32];
-            }
+        }
+        auto U = [&](int q) { return DIRECT ? v[DIRECT ? q : 0] : sv[q * 32]; };
+        auto G = [&](int i) { return gr[MULTI ? 0 : i]; };
+        double tau[NT];
+        if constexpr (MULTI) {
+            tau_dense<N>(M, U, a.mu, tau);
+        } else if constexpr (ORDER == 2) {
+            tau_p2(G, U, a.mu, tau);
         } else {
-#pragma unroll
-            for (int k = 0; k < N; ++k) {
-                v.x[k] = vn.x[k];
-                v.y[k] = vn.y[k];
-                v.z[k] = vn.z[k];
-            }
-            if (j + 1 < npass) prefetch(j + 1);
+            tau_p1(G, U, a.mu, tau);
         }
-        const int col = seg0 + j * K2_COLS + lane - 1;  // lane 0: the column before this pass
-        const bool live = lane > 0 && col < seg1;
-        double tau[9];
-        if (MULTI)
-            tau_dense<ORDER>(M, v, a.mu, tau);
-        else
-            tau_single<ORDER>(g, n, gam, v, a.mu, tau);
-        if (j == 0 && seeded) {  // warp-uniform; lane 0 sits on the column before the block's first (col < 0)
+        const int col = (t0 + j) * 32 + lane;
+        const bool live = col >= a.r0 && col < a.ncol;
+        const bool tw_live = live && !(j == 0 && lane == 0 && y > 0);
+        // w = tau - tau_prev (the 1 / dt is applied to the sums at the end: |.| and P are homogeneous)
+        double dw[NT];
 #pragma unroll
-            for (int i = 0; i < NT; ++i) {
-                const double t = __shfl_sync(0xffffffffu, prev_seed, i);
-                if (lane == 0) tau[i] = t;
+        for (int i = 0; i < NT; ++i) {
+            const double r = __shfl_sync(0xffffffffu, tau[i], (lane + 31) & 31);
+            double prev = r;
+            if constexpr (FLAT) {
+                if (lane == 0) prev = carry[i];
+                carry[i] = r;  // lane 0: tau of lane 31, the predecessor of the next pass's first column
+            } else if (lane == 0) {
+                prev = carry_s[i];
+                carry_s[i] = r;
             }
+            dw[i] = tau[i] - prev;
         }
-        double dw[9];
-#pragma unroll
-        for (int i = 0; i < NT; ++i) dw[i] = (tau[i] - shfl_up1(tau[i])) * a.inv_dt;
-        if (live) {
-            if (FLAT) {
+        if constexpr (FLAT) {
+            const double m = norm3(tau[0], tau[1], tau[2]), mw = norm3(dw[0], dw[1], dw[2]);
+            if (live) {
 #pragma unroll
                 for (int i = 0; i < 3; ++i) acc[i] += tau[i];
-                acc[9] += norm3(tau[0], tau[1], tau[2]);
-                acc[12] += norm3(dw[0], dw[1], dw[2]);
+                acc[3] += m;
+            }
+            if (tw_live) acc[4] += mw;
+        } else {
+            double m[3], p[3];
 #pragma unroll
-                for (int i = 3; i < 9; ++i) tau[i] = tau[i - 3];
-            } else {
-                double p[3];
+            for (int j2 = 0; j2 < 3; ++j2) m[j2] = norm3(tau[3 * j2], tau[3 * j2 + 1], tau[3 * j2 + 2]);
+            twssg_project(dw, p);
+            if (live) {
 #pragma unroll
                 for (int i = 0; i < 9; ++i) acc[i] += tau[i];
 #pragma unroll
-                for (int j2 = 0; j2 < 3; ++j2) acc[9 + j2] += norm3(tau[3 * j2], tau[3 * j2 + 1], tau[3 * j2 + 2]);
-                twssg_project(dw, p);
+                for (int j2 = 0; j2 < 3; ++j2) acc[9 + j2] += m[j2];
+            }
+            if (tw_live) {
 #pragma unroll
                 for (int j2 = 0; j2 < 3; ++j2) acc[12 + j2] += p[j2];
             }
-            if (a.wss_out) {
-                double* o = a.wss_out + ((int64_t)(col - a.r0) * nF + f) * 9;
+        }
+        if (live && a.wss_out) {
+            double* o = a.wss_out + ((int64_t)(col - a.r0) * nF + f) * 9;
 #pragma unroll
-                for (int i = 0; i < 9; ++i) o[i] = tau[i];
-            }
-            if (col == a.ncol - 1) {
+            for (int i = 0; i < 9; ++i) o[i] = tau[FLAT ? i % 3 : i];
+        }
+        if (col == a.ncol - 1) {
 #pragma unroll
-                for (int i = 0; i < 9; ++i) a.tau_last_out[(int64_t)i * nF + f] = tau[i];
-            }
+            for (int i = 0; i < 9; ++i) a.tau_last_out[(int64_t)i * nF + f] = tau[FLAT ? i % 3 : i];
+        }
+        // boundary records for k3_fold: first column (segments after the first), last column
+        if ((j == 0 && lane == 0 && y > 0) || (j == nt - 1 && lane == 31)) {
+            double* b = sg.bnd + ((int64_t)(2 * y + (lane == 0 ? 0 : 1)) * 9) * T.n_work + w;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) b[(int64_t)i * T.n_work] = tau[FLAT ? i % 3 : i];
         }
     }
 
     // fixed-order butterfly over the 32 lanes, then lane 0 stores the segment's partial sums
 #pragma unroll
-    for (int i = 0; i < VH_NSUM; ++i) {
-        if (FLAT && !(i < 3 || i == 9 || i == 12)) continue;
+    for (int i = 0; i < NACC; ++i) {
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], d);
     }
-    if (FLAT) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) acc[3 + i] = acc[6 + i] = acc[i];
-        acc[10] = acc[11] = acc[9];
-        acc[13] = acc[14] = acc[12];
-    }
     if (lane == 0) {
-        double* p = a.part + (int64_t)y * VH_NSUM * T.n_work + w;
+        const double s = fabs(a.inv_dt);
+        double* p = sg.part + (int64_t)y * VH_NSUM * T.n_work + w;
 #pragma unroll
-        for (int i = 0; i < VH_NSUM; ++i) p[(int64_t)i * T.n_work] = acc[i];
+        for (int i = 0; i < VH_NSUM; ++i) {
+            double val;
+            if constexpr (FLAT)
+                val = i < 9 ? acc[i % 3] : i < 12 ? acc[3] : acc[4] * s;
+            else
+                val = i < 12 ? acc[i] : acc[i] * s;
+            p[(int64_t)i * T.n_work] = val;
+        }
     }
 }
 
-// sums[i][f] += part[0][i][w] + part[1][i][w] + ...  for f = work[w], in fixed order; the single-facet and the
-// multi-facet launches have their own segment counts and partial-sum blocks
-__global__ void k3_fold(double* __restrict__ sums, const double* __restrict__ part_s, int gy_s,
-                        const double* __restrict__ part_m, int gy_m, const int32_t* __restrict__ work, int64_t n_work,
-                        int64_t multi_start, int64_t nF, int overwrite) {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+template <int ORDER>
+__global__ void __launch_bounds__(32 * K2_WARPS, K2Launch<ORDER>::MIN_BLOCKS) k2_wall(const K2Args a) {
+    extern __shared__ __align__(16) double k2_smem[];
+    const int nb_multi = a.multi.gx * a.multi.gy;
+    if ((int)blockIdx.x < nb_multi) {
+        k2_body<ORDER, true>(a, a.multi, blockIdx.x % a.multi.gx, blockIdx.x / a.multi.gx, k2_smem);
+    } else {
+        const int b = blockIdx.x - nb_multi;
+        k2_body<ORDER, false>(a, a.single, b % a.single.gx, b / a.single.gx, k2_smem);
+    }
+}
+
+// sums[i][f] (+)= sum over the segments of part[q][i][w], f = work[w], in fixed order, plus the TWSSG terms of the
+// segment boundaries, P(|tau_first(s) - tau_last(s - 1)| / dt), which no segment could form on its own.  The
+// single-facet and the multi-facet launches have their own segment counts and buffers.
+__global__ void k3_fold(double* __restrict__ sums, const double* __restrict__ part_s, const double* __restrict__ bnd_s,
+                        int gy_s, const double* __restrict__ part_m, const double* __restrict__ bnd_m, int gy_m,
+                        const int32_t* __restrict__ work, int64_t n_work, int64_t multi_start, int64_t nF,
+                        double inv_dt, int overwrite) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= VH_NSUM * n_work) return;
-    const int64_t w = idx % n_work, i = idx / n_work;
+    const int64_t w = idx % n_work;
+    const int i = (int)(idx / n_work);
     const int32_t f = work[w];
     if (f < 0) return;
     const bool multi = w >= multi_start;
-    const double* p = (multi ? part_m : part_s) + i * n_work + w;
+    const double* part = (multi ? part_m : part_s) + (int64_t)i * n_work + w;
+    const double* bnd = (multi ? bnd_m : bnd_s) + w;
     const int gq = multi ? gy_m : gy_s;
-    double t = overwrite ? 0.0 : sums[i * nF + f];  // first launch of a time loop: no memset needed
-    for (int q = 0; q < gq; ++q) t += p[(int64_t)q * VH_NSUM * n_work];
-    sums[i * nF + f] = t;
+    double t = overwrite ? 0.0 : sums[(int64_t)i * nF + f];  // first launch of a time loop: no memset needed
+    for (int q = 0; q < gq; ++q) {
+        t += part[(int64_t)q * VH_NSUM * n_work];
+        if (i >= 12 && q > 0) {  // the three TWSSG rows each evaluate the boundary projection and keep their entry
+            double dw[9], p[3];
+#pragma unroll
+            for (int c = 0; c < 9; ++c)
+                dw[c] = bnd[((int64_t)(2 * q) * 9 + c) * n_work] - bnd[((int64_t)(2 * q - 1) * 9 + c) * n_work];
+            twssg_project(dw, p);
+            t += (i == 12 ? p[0] : i == 13 ? p[1] : p[2]) * fabs(inv_dt);
+        }
+    }
+    sums[(int64_t)i * nF + f] = t;
 }
 
 // compute_hemodynamics.py:326-346
@@ -586,6 +650,7 @@ static int ensure_stage_block(vh_handle* h, int64_t want_cols) {
     if (cols > want_cols) cols = want_cols;
     if (cols < 64 && h->batch_snapshots <= 0) cols = 64;
     cols = (cols + 31) / 32 * 32;
+    while (cols > 32 && h->nWn_pad * 3 * cols >= (1LL << 31)) cols -= 32;  // K2 addresses W with int32 element offsets
     if (cols <= cap) return VH_OK;
     if (h->d_W) cudaFree(h->d_W);
     h->d_W = nullptr;
@@ -597,16 +662,16 @@ static int ensure_stage_block(vh_handle* h, int64_t want_cols) {
 
 namespace {
 
-// Segments of one launch: `total` lane passes split as evenly as possible over gy segments.
+// Segments of one launch: the tiles of the block split as evenly as possible over gy segments.
 struct SegPlan {
     int gy, base, extra;
 };
 
-SegPlan plan_segments(int64_t nb, int64_t n_items, int64_t target_warps, int64_t chunk_snapshots) {
-    const int64_t total = (nb + K2_COLS - 1) / K2_COLS;
+SegPlan plan_segments(int64_t ncol, int64_t n_items, int64_t target_warps, int64_t chunk_snapshots) {
+    const int64_t total = (ncol + 31) / 32;
     int64_t gy;
     if (chunk_snapshots > 0) {
-        const int64_t p = (chunk_snapshots + K2_COLS - 1) / K2_COLS;
+        const int64_t p = (chunk_snapshots + 31) / 32;
         gy = (total + p - 1) / p;
     } else {
         gy = n_items > 0 ? (target_warps + n_items - 1) / n_items : 1;
@@ -617,17 +682,28 @@ SegPlan plan_segments(int64_t nb, int64_t n_items, int64_t target_warps, int64_t
     return {(int)gy, (int)(total / gy), (int)(total % gy)};
 }
 
-template <int ORDER, bool MULTI>
-int launch_k2(const K2Args& a, unsigned gx, unsigned gy, cudaStream_t st) {
-    constexpr int smem = k2_smem_bytes<ORDER>();
+template <int ORDER>
+int launch_k2(const K2Args& a, cudaStream_t st) {
+    using L = K2Launch<ORDER>;
     static bool configured = false;  // per instantiation
-    if (!configured && smem > 48 * 1024) {
-        VH_CUDA(cudaFuncSetAttribute(k2_wall<ORDER, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (!configured && L::SMEM_BYTES > 0) {
+        VH_CUDA(cudaFuncSetAttribute(k2_wall<ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES));
+        VH_CUDA(cudaFuncSetAttribute(k2_wall<ORDER>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
-    k2_wall<ORDER, MULTI><<<dim3(gx, gy), 32 * K2_WARPS, smem, st>>>(a);
+    const unsigned blocks = (unsigned)(a.multi.gx * a.multi.gy + a.single.gx * a.single.gy);
+    k2_wall<ORDER><<<blocks, 32 * K2_WARPS, L::SMEM_BYTES, st>>>(a);
     VH_CUDA(cudaGetLastError());
     return VH_OK;
+}
+
+// resident warps per SM (registers and shared memory, see K2Launch)
+int resident_warps(int order) { return K2_WARPS * (order == 1 ? K2Launch<1>::MIN_BLOCKS : K2Launch<2>::MIN_BLOCKS); }
+
+int64_t env_int(const char* name, int64_t dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoll(v) : dflt;
 }
 
 }  // namespace
@@ -637,28 +713,30 @@ int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_el
     const int64_t nF = h->nF;
     VH_TRY(ensure_stage_block(h, n_snap + 1));
     const int64_t n_single = h->multi_start, n_multi = h->n_work - h->multi_start;
-    const unsigned gx_single = (unsigned)((n_single + K2_WARPS - 1) / K2_WARPS);
-    const unsigned gx_multi = (unsigned)((n_multi + K2_WARPS - 1) / K2_WARPS);
+    const int gx_single = (int)((n_single + K2_WARPS - 1) / K2_WARPS);
+    const int gx_multi = (int)((n_multi + K2_WARPS - 1) / K2_WARPS);
+    // (facet, segment) warps per launch: a few waves of the resident warps, so that the tail is short and the
+    // prologue (three dependent loads) of one warp hides behind the passes of the others
+    static const int64_t waves = env_int("VASP_B200_K2_WAVES", 2);
     int64_t pos = 0;
     while (pos < n_snap) {
         const int halo = (pos == 0 && prev_mode == 2) ? 1 : 0;
         int64_t nb = n_snap - pos;
         if (nb + halo > h->w_ld) nb = h->w_ld - halo;
         const int64_t ncol = nb + halo;
-        // the fewest segments that still give every SM ~64 (facet, segment) warps to schedule; the few multi-facet-cell
-        // facets run beside them on a second stream, cut finer so that they never become the tail
-        const SegPlan ps = plan_segments(nb, n_single, (int64_t)h->sm_count * 64, h->chunk_snapshots);
-        const SegPlan pm = plan_segments(nb, n_multi, (int64_t)h->sm_count * 16, h->chunk_snapshots);
-        const int64_t groups = ps.gy + (n_multi ? pm.gy : 0);
+        const int64_t target = (int64_t)h->sm_count * resident_warps(h->order) * waves;
+        const SegPlan ps = plan_segments(ncol, n_single, target, h->chunk_snapshots);
+        // the few multi-facet-cell facets are cut finer and scheduled first, so that they never are the tail
+        const SegPlan pm = plan_segments(ncol, n_multi, target / 4, h->chunk_snapshots);
+        const int64_t groups = (n_single ? ps.gy : 0) + (n_multi ? pm.gy : 0);
         if (groups > h->part_cap) {
             if (h->d_part) cudaFree(h->d_part);
             h->d_part = nullptr;
             h->part_cap = 0;
-            VH_CUDA(cudaMalloc(&h->d_part, sizeof(double) * VH_NSUM * h->n_work * groups));
+            // per segment: 15 partial sums + tau of the first and of the last column (2 x 9)
+            VH_CUDA(cudaMalloc(&h->d_part, sizeof(double) * (VH_NSUM + 18) * h->n_work * groups));
             h->part_cap = groups;
         }
-        double* part_s = h->d_part;
-        double* part_m = h->d_part + (int64_t)ps.gy * VH_NSUM * h->n_work;
         const bool prof = h->profile && h->prof_used + 3 <= h->prof_pool.size();
         if (prof) cudaEventRecord(h->prof_pool[h->prof_used], h->s_compute);
         VH_TRY(k1_launch(h, d_u + (pos - halo) * stride_elems, ncol, stride_elems));
@@ -666,48 +744,33 @@ int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_el
         K2Args a;
         a.T = vh_tables(h);
         a.W = h->d_W;
-        a.ld = h->w_ld;
+        a.ntile_ld = (int)(h->w_ld / 32);
         a.ncol = (int)ncol;
         a.r0 = halo;
         a.prev_mode = pos == 0 ? prev_mode : 1;
+        a.single = {n_single ? gx_single : 0, n_single ? ps.gy : 0, ps.base, ps.extra, h->d_part,
+                    h->d_part + (int64_t)h->part_cap * VH_NSUM * h->n_work};
+        a.multi = {n_multi ? gx_multi : 0, n_multi ? pm.gy : 0, pm.base, pm.extra,
+                   a.single.part + (int64_t)a.single.gy * VH_NSUM * h->n_work,
+                   a.single.bnd + (int64_t)a.single.gy * 18 * h->n_work};
         a.tau_last_in = h->d_tau_last[h->tau_cur];
         a.tau_last_out = h->d_tau_last[h->tau_cur ^ 1];
         h->tau_cur ^= 1;
         a.wss_out = d_wss ? d_wss + pos * nF * 9 : nullptr;
         a.mu = h->mu;
         a.inv_dt = 1.0 / h->dt;
-        if (gx_multi) {  // fork: multi-facet cells on the auxiliary stream, after K1
-            VH_CUDA(cudaEventRecord(h->ev_fork, h->s_compute));
-            VH_CUDA(cudaStreamWaitEvent(h->s_aux, h->ev_fork, 0));
-            a.part = part_m;
-            a.pass_base = pm.base;
-            a.pass_extra = pm.extra;
-            if (h->order == 2)
-                VH_TRY((launch_k2<2, true>(a, gx_multi, pm.gy, h->s_aux)));
-            else
-                VH_TRY((launch_k2<1, true>(a, gx_multi, pm.gy, h->s_aux)));
-            VH_CUDA(cudaEventRecord(h->ev_join, h->s_aux));
-            h->launches += 1;
-        }
-        if (gx_single) {
-            a.part = part_s;
-            a.pass_base = ps.base;
-            a.pass_extra = ps.extra;
-            if (h->order == 2)
-                VH_TRY((launch_k2<2, false>(a, gx_single, ps.gy, h->s_compute)));
-            else
-                VH_TRY((launch_k2<1, false>(a, gx_single, ps.gy, h->s_compute)));
-            h->launches += 1;
-        }
-        if (gx_multi) VH_CUDA(cudaStreamWaitEvent(h->s_compute, h->ev_join, 0));
+        if (h->order == 2)
+            VH_TRY(launch_k2<2>(a, h->s_compute));
+        else
+            VH_TRY(launch_k2<1>(a, h->s_compute));
+        h->launches += 1;
         if (prof) {
             cudaEventRecord(h->prof_pool[h->prof_used + 2], h->s_compute);
             h->prof_used += 3;
         }
-        const int64_t n = VH_NSUM * h->n_work;
-        k3_fold<<<(unsigned)((n + 255) / 256), 256, 0, h->s_compute>>>(h->d_sums, part_s, gx_single ? ps.gy : 0, part_m,
-                                                                       pm.gy, h->d_work, h->n_work, h->multi_start, nF,
-                                                                       h->sums_pending_zero ? 1 : 0);
+        k3_fold<<<(unsigned)((VH_NSUM * h->n_work + 127) / 128), 128, 0, h->s_compute>>>(
+            h->d_sums, a.single.part, a.single.bnd, a.single.gy, a.multi.part, a.multi.bnd, a.multi.gy, h->d_work,
+            h->n_work, h->multi_start, nF, a.inv_dt, h->sums_pending_zero ? 1 : 0);
         h->sums_pending_zero = false;
         VH_CUDA(cudaGetLastError());
         h->launches += 1;
