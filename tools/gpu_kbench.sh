@@ -7,7 +7,7 @@ if [ $# -eq 0 ]; then set -- "stenosis_p1 1000" "stenosis_p2 1000" "aneurysm_p1 
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 for v in $VARS; do
-  export VASP_B200_K2_VARIANT=$v
+  export VASP_B200_K2_VARIANT=$v VASP_B200_K2_FLAT=$v
   timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_v$v.log 2>&1; echo "variant $v: pytest rc=$? $(tail -1 $OUT/pytest_v$v.log)"
   for spec in "$@"; do
     WL=${spec% *}; NS=${spec#* }

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(TILE* ROWS)
 int k1_launch(vh_handle* h, const double* d_u, int64_t ncol, int64_t stride_elems) {
     VH_CHECK(ncol > 0 && ncol <= h->w_ld, VH_ERR_ARG, "k1_launch: %lld columns do not fit the staged block (%lld)",
              (long long)ncol, (long long)h->w_ld);
-    const int64_t gy = (ncol + TILE - 1) / TILE;
+    const int64_t gy = (ncol + 2 * TILE - 1) / (2 * TILE) * 2;  // zero-filled up to whole 64-column passes of K2
     VH_CHECK(gy <= 65535, VH_ERR_ARG, "k1_launch: too many snapshots in one block");
     dim3 grid((unsigned)(h->nWn_pad / TILE), (unsigned)gy), block(TILE, ROWS);
     k1_stage<<<grid, block, 0, h->s_compute>>>(d_u, stride_elems, (int)ncol, h->d_wall_slot, h->comp_offset[0],

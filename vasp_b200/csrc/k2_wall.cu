@@ -53,38 +53,27 @@ constexpr double Q_W0 = 0.225, Q_W1 = 0.12593918054482717, Q_W2 = 0.132394152788
 
 constexpr int K2_WARPS = 4;
 
-// Compile-time shape of one code path (ORDER x single-/multi-facet cell).  How the dof values reach the arithmetic:
-//   P1  DIRECT: ld.global.nc straight into registers (12 doubles), the next tile's loads issued before this tile's
-//       arithmetic (register double buffer)
-//   P2  ring:   cp.async into a per-warp shared-memory landing buffer of two tiles (each lane copies and later reads
-//       only its own column: no barrier); 30 doubles per lane would not fit twice in registers
-// Per-facet constants (grad lambda (12), n (3), gamma (4)) stay in registers.  Alternatives that were measured and
-// dropped: constants or a 3 x 12 traction operator in shared memory to reach 32 warps per SM --
-// every warp-uniform LDS still costs its data-path cycles, the kernel became MIO-bound; a single-stage landing buffer
-// with 20 warps per SM (spills); L1 prefetch two tiles ahead (no effect: W is L2-resident after K1).
-// Shared memory per warp, in doubles: [STAGES][3 N][32] landing buffer | [CARRY] tau of the last lane of the previous
-// pass (touched by lane 0 only).
-template <int ORDER, bool MULTI>
-struct K2Cfg {
-    static constexpr int N = ORDER == 2 ? 10 : 4;
-    // P1 data in a cell with one exterior facet: tau is the same at the three facet vertices, so one magnitude and
-    // P(|w|) = |w| exactly (the projection reproduces constants)
-    static constexpr bool FLAT = ORDER == 1 && !MULTI;
-    static constexpr int NT = FLAT ? 3 : 9;
-    static constexpr bool DIRECT = ORDER == 1;
-    static constexpr bool PREF = DIRECT;
-    static constexpr int STAGES = DIRECT ? 0 : 2;
-    static constexpr int STAGE_DOUBLES = 3 * N * 32;
-    static constexpr int CARRY = FLAT ? 0 : 10;
-    static constexpr int WARP_DOUBLES = STAGES * STAGE_DOUBLES + CARRY;
-};
+// Three code paths share one launch (k2_wall<ORDER>):
+//   k2_body_flat2     P1 data, cell with one exterior facet: values by ld.global.nc straight into registers (register
+//                     double buffer), two snapshots per lane, closed-form traction, constants in registers
+//   k2_body_p2        P2 data, cell with one exterior facet: values by cp.async into a per-warp shared-memory landing
+//                     buffer of two tiles (30 doubles per lane would not fit twice in registers; each lane copies and
+//                     later reads only its own column: no barrier), closed-form traction, constants in registers
+//   k2_body_multi2    cells with several exterior facets: dense operator (K0) staged once per warp in shared memory,
+//                     two snapshots per lane so that every operator entry read feeds two evaluations
+// Alternatives that were measured and dropped: per-facet constants or a 3 x 12 traction operator
+// in shared memory to reach 32 warps per SM -- every warp-uniform LDS still costs its data-path cycles, the kernel
+// became MIO-bound; a single-stage landing buffer with 20 warps per SM (spills); L1 prefetch two tiles ahead (no
+// effect: W is L2-resident after K1); a TMA bulk copy per row (bypasses L1, where neighbouring facets share rows).
+// Shared memory per warp, in doubles.
+constexpr int K2_P2_STAGE = 30 * 32;                 // one tile of the 30 dof components
+constexpr int K2_P2_WARP = 2 * K2_P2_STAGE + 10;    // two stages + tau of the last lane of the previous pass
 template <int ORDER>
 struct K2Launch {
-    static constexpr int WARP_DOUBLES = K2Cfg<ORDER, true>::WARP_DOUBLES > K2Cfg<ORDER, false>::WARP_DOUBLES
-                                            ? K2Cfg<ORDER, true>::WARP_DOUBLES
-                                            : K2Cfg<ORDER, false>::WARP_DOUBLES;
+    static constexpr int NV = ORDER == 2 ? 30 : 12;
+    static constexpr int MULTI_WARP = NV * VH_MROW + 10;  // operator + carry
+    static constexpr int WARP_DOUBLES = ORDER == 2 ? (K2_P2_WARP > MULTI_WARP ? K2_P2_WARP : MULTI_WARP) : MULTI_WARP;
     static constexpr int SMEM_BYTES = K2_WARPS * WARP_DOUBLES * (int)sizeof(double);
-    static constexpr int MIN_BLOCKS = ORDER == 1 ? 4 : 3;  // 128 | 168 registers
 };
 
 // sqrt(x) for x >= 0 without the library's special-case branch: rsqrt seed (MUFU.RSQ64H, ~2^-22), two coupled
@@ -169,27 +158,6 @@ __device__ __forceinline__ void tau_p2(GF G, UF U, double mu, double (&tau)[9]) 
     }
 }
 
-// tau of a facet whose cell owns several exterior facets: dense operator from K0 (SurfaceProjector's block solve
-// folded with the contributing faces), warp-uniform coefficient loads
-template <int N, class UF>
-__device__ __forceinline__ void tau_dense(const double* __restrict__ M, UF U, double mu, double (&tau)[9]) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) tau[i] = 0.0;
-#pragma unroll
-    for (int q = 0; q < 3 * N; ++q) {
-        const double val = U(q);
-        const double2* row = reinterpret_cast<const double2*>(M + q * VH_MROW);
-#pragma unroll
-        for (int h2 = 0; h2 < 5; ++h2) {
-            const double2 m2 = __ldg(row + h2);
-            tau[2 * h2] = fma(m2.x, val, tau[2 * h2]);
-            if (h2 < 4) tau[2 * h2 + 1] = fma(m2.y, val, tau[2 * h2 + 1]);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 9; ++i) tau[i] *= -mu;
-}
-
 // P(|w|) on the boundary triangle: p_j = 12 s_j - 3 sum_i s_i,  s_i = sum_q wq phi_i(x_q) |w(x_q)|   (area cancels)
 __device__ __forceinline__ void twssg_project(const double (&w)[9], double (&p)[3]) {
     double sx = w[0] + w[3] + w[6], sy = w[1] + w[4] + w[7], sz = w[2] + w[5] + w[8];
@@ -244,176 +212,356 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Time reductions of one column of a facet with three distinct vertex tractions: sum tau, sum |tau|, sum P(|dtau|).
+__device__ __forceinline__ void reduce9(const double (&tau)[9], const double (&dw)[9], bool live, bool tw_live,
+                                        double (&acc)[VH_NSUM]) {
+    double m[3], p[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) m[j] = norm3(tau[3 * j], tau[3 * j + 1], tau[3 * j + 2]);
+    twssg_project(dw, p);
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) acc[i] += tau[i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[9 + j] += m[j];
+    }
+    if (tw_live) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[12 + j] += p[j];
+    }
+}
+
+// fixed-order butterfly over the 32 lanes, then lane 0 stores the segment's partial sums (TWSSG rows scaled by 1 / dt)
+__device__ __forceinline__ void store_partials(double (&acc)[VH_NSUM], double* part, int64_t n_work, double inv_dt, int lane) {
+#pragma unroll
+    for (int i = 0; i < VH_NSUM; ++i) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], d);
+    }
+    if (lane == 0) {
+        const double s = fabs(inv_dt);
+#pragma unroll
+        for (int i = 0; i < VH_NSUM; ++i) part[(int64_t)i * n_work] = i < 12 ? acc[i] : acc[i] * s;
+    }
+}
+
 // One warp = one facet x one time segment; the 32 lanes are the 32 columns of a tile of the staged block.
-// MULTI = false: facets whose cell owns no other exterior facet (work[0, multi_start)); MULTI = true: the rest.
-template <int ORDER, bool MULTI>
-__device__ __forceinline__ void k2_body(const K2Args& a, const K2Seg& sg, int bx, int y, double* k2_smem) {
-    using C = K2Cfg<ORDER, MULTI>;
-    constexpr int N = C::N, NT = C::NT, NV = 3 * C::N;
-    constexpr bool FLAT = C::FLAT, DIRECT = C::DIRECT, PREF = C::PREF;
+// P2 data, facets whose cell owns no other exterior facet (work[0, multi_start)).
+__device__ __forceinline__ void k2_body_p2(const K2Args& a, const K2Seg& sg, int bx, int y, double* k2_smem) {
     const FacetTables& T = a.T;
     const int64_t nF = T.nF;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t wi = (int64_t)bx * K2_WARPS + wib;
-    const int64_t w = MULTI ? wi + T.multi_start : wi;
-    if (w >= (MULTI ? T.n_work : T.multi_start)) return;
+    const int64_t w = (int64_t)bx * K2_WARPS + wib;
+    if (w >= T.multi_start) return;
     const int32_t f = T.work[w];
     if (f < 0) return;  // padding entry (warp-uniform)
-
     const int t0 = y * sg.tile_base + min(y, sg.tile_extra);
     const int nt = sg.tile_base + (y < sg.tile_extra ? 1 : 0);
 
-    double* const ring = k2_smem + (size_t)wib * K2Launch<ORDER>::WARP_DOUBLES;
-    double* const carry_s = ring + C::STAGES * C::STAGE_DOUBLES;
+    double* const ring = k2_smem + (size_t)wib * K2Launch<2>::WARP_DOUBLES;
+    double* const carry_s = ring + 2 * K2_P2_STAGE;
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring + lane);
 
     // element offset inside W of (cell dof k, tile t0, component 0, this lane's column); W holds < 2^31 doubles
-    int32_t rb[N];
+    int32_t rb[10];
 #pragma unroll
-    for (int k = 0; k < N; ++k) rb[k] = (T.row[(int64_t)k * nF + f] * a.ntile_ld + t0) * 96 + lane;
-    double v[DIRECT ? NV : 1], vn[PREF ? NV : 1];
-    auto fetch = [&](int j, int stage) {  // tile t0 + j -> landing stage | registers
-        if constexpr (DIRECT) {
+    for (int k = 0; k < 10; ++k) rb[k] = (T.row[(int64_t)k * nF + f] * a.ntile_ld + t0) * 96 + lane;
+    auto fetch = [&](int j) {  // tile t0 + j -> landing stage j & 1
+        const uint32_t dst = ring_s + (uint32_t)((j & 1) * K2_P2_STAGE * sizeof(double));
 #pragma unroll
-            for (int k = 0; k < N; ++k) {
-                const double* p = a.W + (rb[k] + j * 96);
+        for (int k = 0; k < 10; ++k) {
+            const double* p = a.W + (rb[k] + j * 96);
 #pragma unroll
-                for (int d = 0; d < 3; ++d) (PREF ? vn : v)[3 * k + d] = __ldg(p + 32 * d);
-            }
-        } else {
-            const uint32_t dst = ring_s + (uint32_t)(stage * C::STAGE_DOUBLES * sizeof(double));
-#pragma unroll
-            for (int k = 0; k < N; ++k) {
-                const double* p = a.W + (rb[k] + j * 96);
-#pragma unroll
-                for (int d = 0; d < 3; ++d) cp_async8(dst + (3 * k + d) * 256, p + 32 * d);
-            }
-            cp_async_commit();
+            for (int d = 0; d < 3; ++d) cp_async8(dst + (3 * k + d) * 256, p + 32 * d);
         }
+        cp_async_commit();
     };
-    if (PREF || !DIRECT) fetch(0, 0);
+    fetch(0);
 
-    // ---- per-facet constants: {grad lambda [4][3], n [3], gamma [4]} in registers, or the dense operator's address -----
-    const double* M = nullptr;
-    double gr[MULTI ? 1 : 19];
-    if constexpr (MULTI) {
-        M = T.m_mat + (size_t)wi * 3 * N * VH_MROW;
-    } else {
+    // per-facet constants in registers: {grad lambda [4][3], n [3], gamma [4]}
+    double gr[19];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) gr[i] = T.glam[(int64_t)i * nF + f];
+    for (int i = 0; i < 12; ++i) gr[i] = T.glam[(int64_t)i * nF + f];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) gr[12 + d] = T.normal[(int64_t)d * nF + f];
+    for (int d = 0; d < 3; ++d) gr[12 + d] = T.normal[(int64_t)d * nF + f];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) gr[15 + b] = gr[3 * b] * gr[12] + gr[3 * b + 1] * gr[13] + gr[3 * b + 2] * gr[14];
-    }
+    for (int b = 0; b < 4; ++b) gr[15 + b] = gr[3 * b] * gr[12] + gr[3 * b + 1] * gr[13] + gr[3 * b + 2] * gr[14];
     // tau_prev of the segment's first column.  Segment 0: zero, or carried over from the last launch; later
     // segments: unknown here -- lane 0 skips that one TWSSG term and k3_fold adds it from the boundary records.
-    double carry[FLAT ? 3 : 1];
-    if constexpr (FLAT) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-            carry[i] = (y == 0 && a.prev_mode == 1 && lane == 0) ? a.tau_last_in[(int64_t)i * nF + f] : 0.0;
-    } else if (lane == 0) {
+    if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) carry_s[i] = (y == 0 && a.prev_mode == 1) ? a.tau_last_in[(int64_t)i * nF + f] : 0.0;
     }
     __syncwarp();
 
-    constexpr int NACC = FLAT ? 5 : VH_NSUM;
-    double acc[NACC];
+    double acc[VH_NSUM];
 #pragma unroll
-    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+    for (int i = 0; i < VH_NSUM; ++i) acc[i] = 0.0;
 
     for (int j = 0; j < nt; ++j) {
-        const double* sv = ring + (j & 1) * C::STAGE_DOUBLES + lane;  // sv[(3 k + d) * 32]
-        if constexpr (DIRECT) {
-            if constexpr (PREF) {
-#pragma unroll
-                for (int q = 0; q < NV; ++q) v[q] = vn[q];
-                if (j + 1 < nt) fetch(j + 1, 0);
-            } else {
-                fetch(j, 0);
-            }
+        if (j + 1 < nt) {
+            fetch(j + 1);
+            cp_async_wait<1>();
         } else {
-            if (j + 1 < nt) {
-                fetch(j + 1, (j + 1) & 1);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
+            cp_async_wait<0>();
         }
-        auto U = [&](int q) { return DIRECT ? v[DIRECT ? q : 0] : sv[q * 32]; };
-        auto G = [&](int i) { return gr[MULTI ? 0 : i]; };
-        double tau[NT];
-        if constexpr (MULTI) {
-            tau_dense<N>(M, U, a.mu, tau);
-        } else if constexpr (ORDER == 2) {
-            tau_p2(G, U, a.mu, tau);
-        } else {
-            tau_p1(G, U, a.mu, tau);
-        }
+        const double* sv = ring + (j & 1) * K2_P2_STAGE + lane;  // sv[(3 k + d) * 32]
+        double tau[9], dw[9];
+        tau_p2([&](int i) { return gr[i]; }, [&](int q) { return sv[q * 32]; }, a.mu, tau);
         const int col = (t0 + j) * 32 + lane;
         const bool live = col >= a.r0 && col < a.ncol;
-        const bool tw_live = live && !(j == 0 && lane == 0 && y > 0);
         // w = tau - tau_prev (the 1 / dt is applied to the sums at the end: |.| and P are homogeneous)
-        double dw[NT];
 #pragma unroll
-        for (int i = 0; i < NT; ++i) {
+        for (int i = 0; i < 9; ++i) {
             const double r = __shfl_sync(0xffffffffu, tau[i], (lane + 31) & 31);
             double prev = r;
-            if constexpr (FLAT) {
-                if (lane == 0) prev = carry[i];
-                carry[i] = r;  // lane 0: tau of lane 31, the predecessor of the next pass's first column
-            } else if (lane == 0) {
+            if (lane == 0) {
                 prev = carry_s[i];
-                carry_s[i] = r;
+                carry_s[i] = r;  // tau of lane 31: the predecessor of the next pass's first column
             }
             dw[i] = tau[i] - prev;
         }
-        if constexpr (FLAT) {
-            const double m = norm3(tau[0], tau[1], tau[2]), mw = norm3(dw[0], dw[1], dw[2]);
-            if (live) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) acc[i] += tau[i];
-                acc[3] += m;
-            }
-            if (tw_live) acc[4] += mw;
-        } else {
-            double m[3], p[3];
-#pragma unroll
-            for (int j2 = 0; j2 < 3; ++j2) m[j2] = norm3(tau[3 * j2], tau[3 * j2 + 1], tau[3 * j2 + 2]);
-            twssg_project(dw, p);
-            if (live) {
-#pragma unroll
-                for (int i = 0; i < 9; ++i) acc[i] += tau[i];
-#pragma unroll
-                for (int j2 = 0; j2 < 3; ++j2) acc[9 + j2] += m[j2];
-            }
-            if (tw_live) {
-#pragma unroll
-                for (int j2 = 0; j2 < 3; ++j2) acc[12 + j2] += p[j2];
-            }
-        }
+        reduce9(tau, dw, live, live && !(j == 0 && lane == 0 && y > 0), acc);
         if (live && a.wss_out) {
             double* o = a.wss_out + ((int64_t)(col - a.r0) * nF + f) * 9;
 #pragma unroll
-            for (int i = 0; i < 9; ++i) o[i] = tau[FLAT ? i % 3 : i];
+            for (int i = 0; i < 9; ++i) o[i] = tau[i];
         }
         if (col == a.ncol - 1) {
 #pragma unroll
-            for (int i = 0; i < 9; ++i) a.tau_last_out[(int64_t)i * nF + f] = tau[FLAT ? i % 3 : i];
+            for (int i = 0; i < 9; ++i) a.tau_last_out[(int64_t)i * nF + f] = tau[i];
         }
         // boundary records for k3_fold: first column (segments after the first), last column
         if ((j == 0 && lane == 0 && y > 0) || (j == nt - 1 && lane == 31)) {
             double* b = sg.bnd + ((int64_t)(2 * y + (lane == 0 ? 0 : 1)) * 9) * T.n_work + w;
 #pragma unroll
-            for (int i = 0; i < 9; ++i) b[(int64_t)i * T.n_work] = tau[FLAT ? i % 3 : i];
+            for (int i = 0; i < 9; ++i) b[(int64_t)i * T.n_work] = tau[i];
         }
     }
+    store_partials(acc, sg.part + (int64_t)y * VH_NSUM * T.n_work + w, T.n_work, a.inv_dt, lane);
+}
 
-    // fixed-order butterfly over the 32 lanes, then lane 0 stores the segment's partial sums
+// Facets whose cell owns several exterior facets (work[multi_start, n_work)): tau = -mu M^T u with the dense operator
+// K0 built (SurfaceProjector's block solve folded with the contributing faces).  The operator is staged once per warp
+// in shared memory, already scaled by -mu; a pass covers 64 columns, lane l owns columns 2 l and 2 l + 1, so every
+// warp-uniform operator read feeds two evaluations.
+template <int ORDER>
+__device__ __forceinline__ void k2_body_multi2(const K2Args& a, const K2Seg& sg, int bx, int y, double* k2_smem) {
+    constexpr int N = ORDER == 2 ? 10 : 4, NV = 3 * N;
+    const FacetTables& T = a.T;
+    const int64_t nF = T.nF;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t wi = (int64_t)bx * K2_WARPS + wib;
+    const int64_t w = wi + T.multi_start;
+    if (w >= T.n_work) return;
+    const int32_t f = T.work[w];
+    if (f < 0) return;  // padding entry (warp-uniform)
+    const int p0 = y * sg.tile_base + min(y, sg.tile_extra);  // passes of 64 columns
+    const int np = sg.tile_base + (y < sg.tile_extra ? 1 : 0);
+
+    double* const Ms = k2_smem + (size_t)wib * K2Launch<ORDER>::WARP_DOUBLES;  // [NV][VH_MROW]
+    double* const carry_s = Ms + NV * VH_MROW;
+    {
+        const double2* Mg = reinterpret_cast<const double2*>(T.m_mat + (size_t)wi * NV * VH_MROW);
+        const double s = -a.mu;
+        for (int i = lane; i < NV * VH_MROW / 2; i += 32) {
+            double2 m = __ldg(Mg + i);
+            m.x *= s;
+            m.y *= s;
+            reinterpret_cast<double2*>(Ms)[i] = m;
+        }
+        if (lane < 9) carry_s[lane] = (y == 0 && a.prev_mode == 1) ? a.tau_last_in[(int64_t)lane * nF + f] : 0.0;
+    }
+    __syncwarp();
+    // element offset inside W of (cell dof k, tile 2 p0 + lane / 16, component 0, column 2 (lane % 16))
+    int32_t rb[N];
 #pragma unroll
-    for (int i = 0; i < NACC; ++i) {
+    for (int k = 0; k < N; ++k)
+        rb[k] = (T.row[(int64_t)k * nF + f] * a.ntile_ld + 2 * p0 + (lane >> 4)) * 96 + 2 * (lane & 15);
+
+    double acc[VH_NSUM];
+#pragma unroll
+    for (int i = 0; i < VH_NSUM; ++i) acc[i] = 0.0;
+
+    for (int j = 0; j < np; ++j) {
+        double t0[9], t1[9], d0[9], d1[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) t0[i] = t1[i] = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const double2* p = reinterpret_cast<const double2*>(a.W + (rb[k] + j * 192));
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const double2 u = __ldg(p + 16 * d);
+                const double2* row = reinterpret_cast<const double2*>(Ms + (3 * k + d) * VH_MROW);
+#pragma unroll
+                for (int h2 = 0; h2 < 5; ++h2) {
+                    const double2 m2 = row[h2];
+                    t0[2 * h2] = fma(m2.x, u.x, t0[2 * h2]);
+                    t1[2 * h2] = fma(m2.x, u.y, t1[2 * h2]);
+                    if (h2 < 4) {
+                        t0[2 * h2 + 1] = fma(m2.y, u.x, t0[2 * h2 + 1]);
+                        t1[2 * h2 + 1] = fma(m2.y, u.y, t1[2 * h2 + 1]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const double r = __shfl_sync(0xffffffffu, t1[i], (lane + 31) & 31);
+            double prev = r;
+            if (lane == 0) {
+                prev = carry_s[i];
+                carry_s[i] = r;  // tau of the last column of this pass
+            }
+            d0[i] = t0[i] - prev;
+            d1[i] = t1[i] - t0[i];
+        }
+        const int col = 64 * (p0 + j) + 2 * lane;
+        const bool live0 = col >= a.r0 && col < a.ncol, live1 = col + 1 >= a.r0 && col + 1 < a.ncol;
+        reduce9(t0, d0, live0, live0 && !(j == 0 && lane == 0 && y > 0), acc);
+        reduce9(t1, d1, live1, live1, acc);
+        if (a.wss_out) {
+            if (live0) {
+                double* o = a.wss_out + ((int64_t)(col - a.r0) * nF + f) * 9;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) o[i] = t0[i];
+            }
+            if (live1) {
+                double* o = a.wss_out + ((int64_t)(col + 1 - a.r0) * nF + f) * 9;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) o[i] = t1[i];
+            }
+        }
+        if (col == a.ncol - 1 || col + 1 == a.ncol - 1) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) a.tau_last_out[(int64_t)i * nF + f] = col == a.ncol - 1 ? t0[i] : t1[i];
+        }
+        // boundary records for k3_fold: first column (segments after the first), last column
+        if (j == 0 && lane == 0 && y > 0) {
+            double* b = sg.bnd + ((int64_t)(2 * y) * 9) * T.n_work + w;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) b[(int64_t)i * T.n_work] = t0[i];
+        }
+        if (j == np - 1 && lane == 31) {
+            double* b = sg.bnd + ((int64_t)(2 * y + 1) * 9) * T.n_work + w;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) b[(int64_t)i * T.n_work] = t1[i];
+        }
+    }
+    store_partials(acc, sg.part + (int64_t)y * VH_NSUM * T.n_work + w, T.n_work, a.inv_dt, lane);
+}
+
+// P1 data in a cell with one exterior facet, TWO consecutive snapshots per lane: a pass covers two tiles (64 columns),
+// lane l owns columns 2 l and 2 l + 1 (one 16-byte load per dof component; the lower half-warp reads the first tile,
+// the upper one the second).  The per-facet constants are shared by two independent evaluations -- twice the
+// instruction-level parallelism per register -- tau_prev of the second column is the lane's own first column, and the
+// shuffles and the integer work per unit halve.  (The fp64 pipe of an SM retires 2 warp instructions per clock at 8
+// clocks latency, measured with tools/ubench/fp64_lat.cu; with 4 warps per scheduler and one column per lane the
+// kernel issued 0.57 instructions per clock.)
+__device__ __forceinline__ void k2_body_flat2(const K2Args& a, const K2Seg& sg, int bx, int y) {
+    const FacetTables& T = a.T;
+    const int64_t nF = T.nF;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t w = (int64_t)bx * K2_WARPS + wib;
+    if (w >= T.multi_start) return;
+    const int32_t f = T.work[w];
+    if (f < 0) return;  // padding entry (warp-uniform)
+    const int p0 = y * sg.tile_base + min(y, sg.tile_extra);  // passes of 64 columns
+    const int np = sg.tile_base + (y < sg.tile_extra ? 1 : 0);
+
+    // element offset inside W of (cell dof k, tile 2 p0 + lane / 16, component 0, column 2 (lane % 16))
+    int32_t rb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        rb[k] = (T.row[(int64_t)k * nF + f] * a.ntile_ld + 2 * p0 + (lane >> 4)) * 96 + 2 * (lane & 15);
+    double2 v[12], vn[12];  // register double buffer: the next pass's loads are issued before this pass's arithmetic
+    auto fetch = [&](int j, double2* dst) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double2* p = reinterpret_cast<const double2*>(a.W + (rb[k] + j * 192));
+#pragma unroll
+            for (int d = 0; d < 3; ++d) dst[3 * k + d] = __ldg(p + 16 * d);
+        }
+    };
+    fetch(0, vn);
+
+    double gr[19];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) gr[i] = T.glam[(int64_t)i * nF + f];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) gr[12 + d] = T.normal[(int64_t)d * nF + f];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) gr[15 + b] = gr[3 * b] * gr[12] + gr[3 * b + 1] * gr[13] + gr[3 * b + 2] * gr[14];
+    auto G = [&](int i) { return gr[i]; };
+
+    // tau_prev of the segment's first column (see k2_body)
+    double carry[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        carry[i] = (y == 0 && a.prev_mode == 1 && lane == 0) ? a.tau_last_in[(int64_t)i * nF + f] : 0.0;
+
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int j = 0; j < np; ++j) {
+#pragma unroll
+        for (int q = 0; q < 12; ++q) v[q] = vn[q];
+        if (j + 1 < np) fetch(j + 1, vn);
+        double t0[3], t1[3], d0[3], d1[3];
+        tau_p1(G, [&](int q) { return v[q].x; }, a.mu, t0);
+        tau_p1(G, [&](int q) { return v[q].y; }, a.mu, t1);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double r = __shfl_sync(0xffffffffu, t1[i], (lane + 31) & 31);
+            d0[i] = t0[i] - (lane == 0 ? carry[i] : r);
+            carry[i] = r;  // lane 0: tau of the last column of this pass
+            d1[i] = t1[i] - t0[i];
+        }
+        const double m0 = norm3(t0[0], t0[1], t0[2]), m1 = norm3(t1[0], t1[1], t1[2]);
+        const double w0 = norm3(d0[0], d0[1], d0[2]), w1 = norm3(d1[0], d1[1], d1[2]);
+        const int col = 64 * (p0 + j) + 2 * lane;
+        const bool live0 = col >= a.r0 && col < a.ncol, live1 = col + 1 >= a.r0 && col + 1 < a.ncol;
+        if (live0) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) acc[i] += t0[i];
+            acc[3] += m0;
+        }
+        if (live0 && !(j == 0 && lane == 0 && y > 0)) acc[4] += w0;
+        if (live1) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) acc[i] += t1[i];
+            acc[3] += m1;
+            acc[4] += w1;
+        }
+        if (a.wss_out) {
+            if (live0) {
+                double* o = a.wss_out + ((int64_t)(col - a.r0) * nF + f) * 9;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) o[i] = t0[i % 3];
+            }
+            if (live1) {
+                double* o = a.wss_out + ((int64_t)(col + 1 - a.r0) * nF + f) * 9;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) o[i] = t1[i % 3];
+            }
+        }
+        if (col == a.ncol - 1 || col + 1 == a.ncol - 1) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) a.tau_last_out[(int64_t)i * nF + f] = (col == a.ncol - 1 ? t0 : t1)[i % 3];
+        }
+        // boundary records for k3_fold: first column (segments after the first), last column
+        if (j == 0 && lane == 0 && y > 0) {
+            double* b = sg.bnd + ((int64_t)(2 * y) * 9) * T.n_work + w;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) b[(int64_t)i * T.n_work] = t0[i % 3];
+        }
+        if (j == np - 1 && lane == 31) {
+            double* b = sg.bnd + ((int64_t)(2 * y + 1) * 9) * T.n_work + w;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) b[(int64_t)i * T.n_work] = t1[i % 3];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], d);
     }
@@ -421,26 +569,22 @@ __device__ __forceinline__ void k2_body(const K2Args& a, const K2Seg& sg, int bx
         const double s = fabs(a.inv_dt);
         double* p = sg.part + (int64_t)y * VH_NSUM * T.n_work + w;
 #pragma unroll
-        for (int i = 0; i < VH_NSUM; ++i) {
-            double val;
-            if constexpr (FLAT)
-                val = i < 9 ? acc[i % 3] : i < 12 ? acc[3] : acc[4] * s;
-            else
-                val = i < 12 ? acc[i] : acc[i] * s;
-            p[(int64_t)i * T.n_work] = val;
-        }
+        for (int i = 0; i < VH_NSUM; ++i) p[(int64_t)i * T.n_work] = i < 9 ? acc[i % 3] : i < 12 ? acc[3] : acc[4] * s;
     }
 }
 
 template <int ORDER>
-__global__ void __launch_bounds__(32 * K2_WARPS, K2Launch<ORDER>::MIN_BLOCKS) k2_wall(const K2Args a) {
+__global__ void __launch_bounds__(32 * K2_WARPS, 3) k2_wall(const K2Args a) {
     extern __shared__ __align__(16) double k2_smem[];
     const int nb_multi = a.multi.gx * a.multi.gy;
     if ((int)blockIdx.x < nb_multi) {
-        k2_body<ORDER, true>(a, a.multi, blockIdx.x % a.multi.gx, blockIdx.x / a.multi.gx, k2_smem);
+        k2_body_multi2<ORDER>(a, a.multi, blockIdx.x % a.multi.gx, blockIdx.x / a.multi.gx, k2_smem);
     } else {
         const int b = blockIdx.x - nb_multi;
-        k2_body<ORDER, false>(a, a.single, b % a.single.gx, b / a.single.gx, k2_smem);
+        if constexpr (ORDER == 1)
+            k2_body_flat2(a, a.single, b % a.single.gx, b / a.single.gx);
+        else
+            k2_body_p2(a, a.single, b % a.single.gx, b / a.single.gx, k2_smem);
     }
 }
 
@@ -649,8 +793,8 @@ static int ensure_stage_block(vh_handle* h, int64_t want_cols) {
     if (cols > 4096) cols = 4096;
     if (cols > want_cols) cols = want_cols;
     if (cols < 64 && h->batch_snapshots <= 0) cols = 64;
-    cols = (cols + 31) / 32 * 32;
-    while (cols > 32 && h->nWn_pad * 3 * cols >= (1LL << 31)) cols -= 32;  // K2 addresses W with int32 element offsets
+    cols = (cols + 63) / 64 * 64;  // whole 64-column passes (two tiles)
+    while (cols > 64 && h->nWn_pad * 3 * cols >= (1LL << 31)) cols -= 64;  // K2 addresses W with int32 element offsets
     if (cols <= cap) return VH_OK;
     if (h->d_W) cudaFree(h->d_W);
     h->d_W = nullptr;
@@ -667,11 +811,11 @@ struct SegPlan {
     int gy, base, extra;
 };
 
-SegPlan plan_segments(int64_t ncol, int64_t n_items, int64_t target_warps, int64_t chunk_snapshots) {
-    const int64_t total = (ncol + 31) / 32;
+SegPlan plan_segments(int64_t ncol, int64_t pass_cols, int64_t n_items, int64_t target_warps, int64_t chunk_snapshots) {
+    const int64_t total = (ncol + pass_cols - 1) / pass_cols;
     int64_t gy;
     if (chunk_snapshots > 0) {
-        const int64_t p = (chunk_snapshots + 31) / 32;
+        const int64_t p = (chunk_snapshots + pass_cols - 1) / pass_cols;
         gy = (total + p - 1) / p;
     } else {
         gy = n_items > 0 ? (target_warps + n_items - 1) / n_items : 1;
@@ -699,7 +843,7 @@ int launch_k2(const K2Args& a, cudaStream_t st) {
 }
 
 // resident warps per SM (registers and shared memory, see K2Launch)
-int resident_warps(int order) { return K2_WARPS * (order == 1 ? K2Launch<1>::MIN_BLOCKS : K2Launch<2>::MIN_BLOCKS); }
+constexpr int K2_RESIDENT_WARPS = 3 * K2_WARPS;
 
 int64_t env_int(const char* name, int64_t dflt) {
     const char* v = getenv(name);
@@ -724,10 +868,10 @@ int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_el
         int64_t nb = n_snap - pos;
         if (nb + halo > h->w_ld) nb = h->w_ld - halo;
         const int64_t ncol = nb + halo;
-        const int64_t target = (int64_t)h->sm_count * resident_warps(h->order) * waves;
-        const SegPlan ps = plan_segments(ncol, n_single, target, h->chunk_snapshots);
+        const int64_t target = (int64_t)h->sm_count * K2_RESIDENT_WARPS * waves;
+        const SegPlan ps = plan_segments(ncol, h->order == 1 ? 64 : 32, n_single, target, h->chunk_snapshots);
         // the few multi-facet-cell facets are cut finer and scheduled first, so that they never are the tail
-        const SegPlan pm = plan_segments(ncol, n_multi, target / 4, h->chunk_snapshots);
+        const SegPlan pm = plan_segments(ncol, 64, n_multi, target / 4, h->chunk_snapshots);
         const int64_t groups = (n_single ? ps.gy : 0) + (n_multi ? pm.gy : 0);
         if (groups > h->part_cap) {
             if (h->d_part) cudaFree(h->d_part);
@@ -753,6 +897,9 @@ int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_el
         a.multi = {n_multi ? gx_multi : 0, n_multi ? pm.gy : 0, pm.base, pm.extra,
                    a.single.part + (int64_t)a.single.gy * VH_NSUM * h->n_work,
                    a.single.bnd + (int64_t)a.single.gy * 18 * h->n_work};
+        static const int skip = (int)env_int("VASP_B200_K2_SKIP", 0);  // timing experiments only (wrong results)
+        if (skip == 1) a.multi.gx = a.multi.gy = 0;
+        if (skip == 2) a.single.gx = a.single.gy = 0;
         a.tau_last_in = h->d_tau_last[h->tau_cur];
         a.tau_last_out = h->d_tau_last[h->tau_cur ^ 1];
         h->tau_cur ^= 1;
