@@ -260,9 +260,13 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     eng.sync()
     if comm:
         comm.barrier()
+    e2e_h2d_ms = e2e_kernel_ms = 0.0
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         out = step_e2e()
+        tm = eng.timers()  # per time loop (vh_begin resets them): CUDA-event sums over the batches of the push
+        e2e_h2d_ms += tm["h2d_ms"] / e2e_steps        # copy stream
+        e2e_kernel_ms += tm["kernel_ms"] / e2e_steps  # compute stream (overlaps the copies)
     eng.sync()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     if comm:
@@ -312,7 +316,9 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                    "results_sane": sane},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps},
+                "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps, "h2d_ms_per_step": e2e_h2d_ms,
+                "h2d_gbs": h2d_bytes / (e2e_h2d_ms * 1e-3) / 1e9 if e2e_h2d_ms > 0 else None,
+                "kernel_ms_per_step": e2e_kernel_ms},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": f"k2_wall<{order}>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -176,6 +176,8 @@ int vh_destroy(vh_handle* h) {
     cudaEventDestroy(h->ev_k0);
     cudaEventDestroy(h->ev_k1);
     for (auto& e : h->prof_pool) cudaEventDestroy(e);
+    for (auto& e : h->batch_events) cudaEventDestroy(e);
+    if (h->h_out5) cudaFreeHost(h->h_out5);
     cudaEventDestroy(h->ev_fork);
     cudaEventDestroy(h->ev_join);
     cudaStreamDestroy(h->s_compute);
@@ -299,6 +301,21 @@ int vh_set_tuning(vh_handle* h, int64_t batch_snapshots, int64_t chunk_snapshots
     return VH_OK;
 }
 
+// D2H of the five result fields: one copy into a pinned staging buffer (user arrays are usually pageable numpy
+// memory, where every cudaMemcpyAsync degenerates into a staged synchronous copy), then host memcpy
+static int export_out5(vh_handle* h, double* const outs[5]) {
+    const int64_t n3 = 3 * h->nF;
+    bool any = false;
+    for (int i = 0; i < 5; ++i) any = any || outs[i];
+    if (!any) return VH_OK;  // results stay in HBM, the call stays asynchronous
+    if (!h->h_out5) VH_CUDA(cudaHostAlloc((void**)&h->h_out5, sizeof(double) * 5 * n3, cudaHostAllocDefault));
+    VH_CUDA(cudaMemcpyAsync(h->h_out5, h->d_out5, sizeof(double) * 5 * n3, cudaMemcpyDeviceToHost, h->s_compute));
+    VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    for (int i = 0; i < 5; ++i)
+        if (outs[i]) memcpy(outs[i], h->h_out5 + i * n3, sizeof(double) * n3);
+    return VH_OK;
+}
+
 static int prev_mode_for(vh_handle* h, int flags, const char* who, int* mode) {
     if (flags & VH_PUSH_HALO_FIRST) {
         *mode = 2;
@@ -370,10 +387,16 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
         h->wss_stage_cap = h->stage_cap;
     }
 
-    std::vector<cudaEvent_t> evs;  // (h2d start, h2d stop, kernel start, kernel stop) per batch
+    // (h2d start, h2d stop, kernel start, kernel stop) per batch, from a pool that lives with the handle: creating
+    // and destroying events inside the call cost more than a batch's kernels on small meshes
+    size_t ev_used = 0;
     auto new_event = [&](cudaEvent_t* e) -> int {
-        VH_CUDA(cudaEventCreate(e));
-        evs.push_back(*e);
+        if (ev_used == h->batch_events.size()) {
+            cudaEvent_t ne;
+            VH_CUDA(cudaEventCreate(&ne));
+            h->batch_events.push_back(ne);
+        }
+        *e = h->batch_events[ev_used++];
         return VH_OK;
     };
     int64_t pos = 0, real_done = 0;
@@ -389,9 +412,14 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
         // copy stream: wait until the kernel that last read this buffer is done, then H2D
         cudaStreamWaitEvent(h->s_copy, h->ev_consumed[buf], 0);
         cudaEventRecord(c0, h->s_copy);
-        cudaError_t ce = cudaMemcpy2DAsync(h->d_stage[buf], (size_t)vec_bytes, (const char*)u + pos * stride_bytes,
-                                           (size_t)stride_bytes, (size_t)vec_bytes, (size_t)nb, cudaMemcpyHostToDevice,
-                                           h->s_copy);
+        // contiguous rows (the usual case: one block of u.h5 vectors) go as one flat copy
+        cudaError_t ce =
+            stride_bytes == vec_bytes
+                ? cudaMemcpyAsync(h->d_stage[buf], (const char*)u + pos * stride_bytes, (size_t)(nb * vec_bytes),
+                                  cudaMemcpyHostToDevice, h->s_copy)
+                : cudaMemcpy2DAsync(h->d_stage[buf], (size_t)vec_bytes, (const char*)u + pos * stride_bytes,
+                                    (size_t)stride_bytes, (size_t)vec_bytes, (size_t)nb, cudaMemcpyHostToDevice,
+                                    h->s_copy);
         if (ce != cudaSuccess) {
             vh_set_error("vh_push_snapshots: H2D copy failed: %s", cudaGetErrorString(ce));
             rc = VH_ERR_CUDA;
@@ -433,12 +461,12 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
         vh_set_error("vh_push_snapshots: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
         rc = VH_ERR_CUDA;
     }
-    for (size_t i = 0; i + 3 < evs.size() && rc == VH_OK; i += 4) {
+    for (size_t i = 0; i + 3 < ev_used && rc == VH_OK; i += 4) {
         float ms = 0.f;
+        const std::vector<cudaEvent_t>& evs = h->batch_events;
         if (cudaEventElapsedTime(&ms, evs[i], evs[i + 1]) == cudaSuccess) h->h2d_ms += ms;
         if (cudaEventElapsedTime(&ms, evs[i + 2], evs[i + 3]) == cudaSuccess) h->kernel_ms += ms;
     }
-    for (cudaEvent_t e : evs) cudaEventDestroy(e);
     return rc;
 }
 
@@ -493,18 +521,10 @@ int vh_finalize(vh_handle* h, int64_t n_total, double* tawss, double* osi, doubl
     VH_TRY(check_ready(h, "vh_finalize"));
     VH_CHECK(n_total > 0, VH_ERR_ARG, "vh_finalize: n_total must be positive");
     VH_TRY(settle_sums(h));
-    const int64_t n3 = 3 * h->nF;
     VH_TRY(k4_finalize(h, n_total, h->d_out5));
-    double* outs[5] = {tawss, osi, rrt, ecap, twssg};
-    bool any = false;
-    for (int i = 0; i < 5; ++i) {
-        if (!outs[i]) continue;
-        any = true;
-        VH_CUDA(cudaMemcpyAsync(outs[i], h->d_out5 + i * n3, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->s_compute));
-    }
+    double* const outs[5] = {tawss, osi, rrt, ecap, twssg};
     // with no host outputs the call stays asynchronous (device-resident timing); results remain in HBM
-    if (any) VH_CUDA(cudaStreamSynchronize(h->s_compute));
-    return VH_OK;
+    return export_out5(h, outs);
 }
 
 int vh_sync(vh_handle* h) {
@@ -780,7 +800,6 @@ int vh_peer_reduce_finalize(vh_handle* h, int64_t n_total, double* tawss, double
     VH_CHECK(h->peer_ready, VH_ERR_ARG, "vh_peer_reduce_finalize: call vh_peer_init first");
     VH_CHECK(n_total > 0, VH_ERR_ARG, "vh_peer_reduce_finalize: n_total must be positive");
     VH_TRY(settle_sums(h));
-    const int64_t n3 = 3 * h->nF;
     PeerBlocks pb;
     for (int q = 0; q < VH_MAX_PEERS; ++q) pb.block[q] = h->peer_block[q];
     const int64_t half_off = (int64_t)h->loop_parity * h->sum_stride, flags_off = 2 * h->sum_stride;
@@ -789,15 +808,8 @@ int vh_peer_reduce_finalize(vh_handle* h, int64_t n_total, double* tawss, double
     VH_TRY(k4_peer_reduce_finalize(h, pb, half_off, flags_off, h->peer_epoch, n_total, h->d_sums_red, h->d_out5));
     h->sums_reduced = true;
     h->count_on_device = true;
-    double* outs[5] = {tawss, osi, rrt, ecap, twssg};
-    bool any = false;
-    for (int i = 0; i < 5; ++i) {
-        if (!outs[i]) continue;
-        any = true;
-        VH_CUDA(cudaMemcpyAsync(outs[i], h->d_out5 + i * n3, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->s_compute));
-    }
-    if (any) VH_CUDA(cudaStreamSynchronize(h->s_compute));
-    return VH_OK;
+    double* const outs[5] = {tawss, osi, rrt, ecap, twssg};
+    return export_out5(h, outs);
 }
 
 int vh_nccl_destroy(vh_handle* h) {

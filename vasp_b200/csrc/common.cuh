@@ -115,6 +115,8 @@ struct vh_handle {
     double* d_tau_last[2] = {nullptr, nullptr};  // [9][nF], ping-pong (read by first chunk, written by last)
     int tau_cur = 0;
     double* d_out5 = nullptr;      // [5][3*nF] TAWSS, OSI, RRT, ECAP, TWSSG
+    double* h_out5 = nullptr;      // pinned staging copy of d_out5 for the D2H export
+    std::vector<cudaEvent_t> batch_events;  // timing events of vh_push_snapshots, reused across calls
     double* d_part = nullptr;      // [groups][15][nF] partial sums of one launch
     int64_t part_cap = 0;          // capacity in groups
     int64_t batch_snapshots = 0, chunk_snapshots = 0;

@@ -763,6 +763,8 @@ int k_free_run_buffers(vh_handle* h) {
     if (h->d_tau_last[1]) cudaFree(h->d_tau_last[1]);
     if (h->d_part) cudaFree(h->d_part);
     if (h->d_out5) cudaFree(h->d_out5);
+    if (h->h_out5) cudaFreeHost(h->h_out5);
+    h->h_out5 = nullptr;
     h->d_sums = h->d_tau_last[0] = h->d_tau_last[1] = h->d_part = h->d_out5 = nullptr;
     h->part_cap = 0;
     for (int i = 0; i < 2; ++i) {
