@@ -290,6 +290,13 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     achieved = units_per_launch * b_alg / (k2_avg_ms * 1e-3) / 1e9
     # K1 (staging) moves 8 B x 3 components per wall-layer node and snapshot, read once and written once
     k1_bytes = 2 * 24 * eng.n_wall_nodes * (n_snap + halo) * args.steps / max(k2_n, 1)
+    # ... but a gather fetches whole 32-byte DRAM sectors: count the distinct sectors the wall-layer nodes occupy in a
+    # snapshot vector (the numbering of the synthetic meshes is randomly permuted on purpose, so a wall-layer node
+    # rarely shares its sector with another one)
+    wall_nodes = np.unique(eng.maps()["facet_nodes"])
+    n_all = len(wl["points"])
+    sectors = sum(np.unique((c * n_all + wall_nodes) // 4).size for c in range(3))
+    k1_sector_bytes = (32 * sectors + 24 * eng.n_wall_nodes) * (n_snap + halo) * args.steps / max(k2_n, 1)
     traffic = None
     tfile = ROOT / "profiles" / "k2_traffic.json"  # written from an `ncu --set full` capture of this command
     if tfile.exists():
@@ -328,7 +335,10 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                                       "bytes_per_launch": k1_bytes,
                                       "achieved": k1_bytes / (k1_avg_ms * 1e-3) / 1e9 if k1_avg_ms > 0 else None,
                                       "frac": k1_bytes / (k1_avg_ms * 1e-3) / 1e9 / peak if k1_avg_ms > 0 else None,
-                                      "wall_nodes": eng.n_wall_nodes}},
+                                      "wall_nodes": eng.n_wall_nodes,
+                                      "sector_bytes_per_launch": k1_sector_bytes,
+                                      "frac_sectors": (k1_sector_bytes / (k1_avg_ms * 1e-3) / 1e9 / peak
+                                                       if k1_avg_ms > 0 else None)}},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
