@@ -10,23 +10,16 @@
 //   TWSSG += project_dg(|dtau/dt|)       (:309-312) 7-point degree-5 rule, closed-form P1 mass inverse
 // and the final formulas (:326-346).
 //
-// Work decomposition: one WARP per (facet, time segment); the 32 LANES are the 32 snapshots of one time TILE of the
-// staged block W that K1 wrote (W[node][tile][component][32], 768 contiguous bytes per node and tile).  Every load of
-// a cell dof is 32 consecutive, 256-byte-aligned doubles; the three components sit at immediate offsets.  The rows of
-// a tile land in a per-warp shared-memory buffer by cp.async (each lane copies and later reads only its own column,
-// so no barrier): two stages for P1 (the next tile is in flight while this one is computed), one stage refilled as
-// soon as its last read is done for P2 (its 7.5 KB per warp would otherwise halve the occupancy).  Per-facet constants
-// live in shared memory too (warp-uniform broadcast reads): for P1 data in a cell with one exterior facet the whole
-// traction is a 3 x 12 operator built in the prologue; for P2 the 19 geometry numbers of the closed form.  That keeps
-// the kernels at 64 (P1) / ~100 (P2) registers, i.e. 32 / 20 warps per SM: the ncu captures of the previous version
-// (profiles/r1k_*) showed a latency-bound kernel -- fixed-latency fp64 dependency stalls with 3-4 warps per scheduler
-// -- not a bandwidth-bound one.
+// Work decomposition: one WARP per (facet, time segment); the LANES are the snapshots of a time tile of the staged
+// block W that K1 wrote (W[node][tile][component][32], 768 contiguous bytes per node and tile).  Every load of a cell
+// dof is a run of consecutive, 256-byte-aligned doubles; the three components sit at immediate offsets.  Three code
+// paths share one launch (see the table before k2_body_p2); DESIGN.md section 3 has what bounds them (fp64 issue, not
+// HBM: W is L2-resident after K1 and each row is shared by ~5 facets) and the variants that were measured and dropped.
 //
-// TWSSG's one-step dependence: inside a tile tau of the previous snapshot comes from the neighbouring lane (shuffle),
-// across tiles lane 0 keeps the last lane's tau of the previous pass, and across SEGMENTS nothing is communicated:
-// each segment records tau of its first and last column and k3_fold adds the missing boundary terms
-// P(|tau_first(s) - tau_last(s-1)| / dt) when it folds the segments' partial sums -- in fixed order, so results are
-// bitwise reproducible for a given launch shape.  Facets of multi-facet cells get their own launch (no divergence).
+// TWSSG's one-step dependence: inside a pass tau of the previous snapshot comes from the neighbouring lane (shuffle),
+// across passes lane 0 keeps the last lane's tau, and across SEGMENTS nothing is communicated: each segment records tau
+// of its first and last column and k3_fold adds the missing boundary terms P(|tau_first(s) - tau_last(s-1)| / dt) when
+// it folds the segments' partial sums -- in fixed order, so results are bitwise reproducible for a given launch shape.
 //
 // Local vertex labels are facet-canonical (K0): 0,1,2 = the facet's vertices in boundary-cell order, 3 = the
 // opposite vertex; P2 edge dofs 4..9 = e01,e02,e12,e03,e13,e23.
