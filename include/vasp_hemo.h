@@ -60,7 +60,10 @@ int vh_set_mesh(vh_handle* h, const double* xyz, int64_t nv, const int64_t* tets
  *   order = 1: refined_xyz may be NULL (velocity lives on the mesh vertices, n_nodes = nv).
  * node_perm (n_nodes int64, may be NULL = identity) maps a velocity node to its slot in the vector; component c
  * of node v is read at  vec[comp_offset[c] + node_stride * node_perm[v]]  (u.h5 written by create_hdf5.py:158-174
- * is comp_offset = {0, n, 2n}, node_stride = 1; dolfin's reordered layout is {0,1,2}, 3). */
+ * is comp_offset = {0, n, 2n}, node_stride = 1; dolfin's reordered layout is {0,1,2}, 3).  node_perm may also be an
+ * injection into a longer vector: a raw turtleFSI array VisualisationVector/<i> of shape (N_all, 3) is read in
+ * place with node_perm = fluid node ids, comp_offset = {0,1,2}, node_stride = 3 (what create_hdf5.py:150-163 slices
+ * on the host); a snapshot vector then has comp_offset_max + node_stride * max(node_perm) + 1 entries. */
 int vh_set_velocity_layout(vh_handle* h, int order, const double* refined_xyz, int64_t n_nodes, double tol,
                            const int64_t* node_perm, const int64_t comp_offset[3], int64_t node_stride);
 

@@ -94,3 +94,55 @@ def test_pulsatile_series_matches_oracle_through_the_cli(tmp_path):
         assert H.rel_l2(got, res["wss"][k]) < 1e-10
     topo = io_dolfin.read_checkpoint(hemo, "WSS", 0)["topology"]
     assert np.array_equal(topo, S.maps.btopology)
+
+
+def test_raw_turtlefsi_output_gives_the_same_fields_as_u_h5(tmp_path):
+    """No ``Visualization_separate_domain``: the reference would run create_hdf5() first (:389-431); here the raw
+    ``VisualisationVector`` arrays (whole domain, interleaved, restarted run in two files) are sliced on the GPU.
+    The result must be bit-identical to the run over the u.h5 that create_hdf5 would have written."""
+    basis_cache = {}
+
+    def u_syn(p, t):
+        if "b" not in basis_cache:
+            basis_cache["b"] = synth.velocity_basis(p, seed=4)
+        coef = np.array([[1 + 0.5 * np.sin(2 * np.pi * t), 0.3 * np.sin(4 * np.pi * t + 1), 0.2 * np.cos(6 * np.pi * t),
+                          0.1 * np.sin(2 * np.pi * t + 2)]])
+        return synth.velocity_series(basis_cache["b"], coef)[0]
+
+    raw = tmp_path / "raw"
+    raw.mkdir()
+    info = H.write_turtle_folder(raw, u_syn, n_snap=11, dt=0.01, mu=3.5e-3, save_step=5, split_at=6)
+    out = subprocess.check_output([sys.executable, "-m", "vasp_b200.compute_hemodynamics", "--folder", str(raw)],
+                                  cwd=ROOT, text=True)
+    assert "Visualization_separate_domain folder not found" in out and "save_time_step: 0.05" in out
+    assert not (raw / "Visualization_separate_domain").exists()
+    # the converted layout of the same series
+    conv = tmp_path / "conv"
+    conv.mkdir()
+    for sub in ("Mesh", "Checkpoint"):
+        (conv / sub).mkdir()
+        for f in (raw / sub).iterdir():
+            (conv / sub / f.name).write_bytes(f.read_bytes())
+    (conv / "Visualization_separate_domain").mkdir()
+    io_dolfin.write_velocity_series(conv / "Visualization_separate_domain" / "u.h5", info["rt"], len(info["rx"]),
+                                    info["vecs"], info["times"])
+    subprocess.check_output([sys.executable, "-m", "vasp_b200.compute_hemodynamics", "--folder", str(conv)],
+                            cwd=ROOT, text=True)
+    for name in H.FIELDS:
+        a = io_dolfin.read_checkpoint(raw / "Hemodynamic_indices", name, 0)["values"]
+        b = io_dolfin.read_checkpoint(conv / "Hemodynamic_indices", name, 0)["values"]
+        assert np.array_equal(a, b), name
+    for k in (0, 10):
+        a = io_dolfin.read_checkpoint(raw / "Hemodynamic_indices", "WSS", k)["values"]
+        b = io_dolfin.read_checkpoint(conv / "Hemodynamic_indices", "WSS", k)["values"]
+        assert np.array_equal(a, b)
+    # and against the oracle
+    cn, edges = ho.p2_cell_nodes(info["tets"])
+    node_of_p2 = ho.match_points(ho.p2_node_coordinates(info["xyz"], edges), info["rx"], 1e-9)
+    S = ho.SurfaceStress(info["xyz"], info["tets"], 3.5e-3, 2, node_of_p2)
+    n = len(info["rx"])
+    res = ho.run_time_loop(S, info["vecs"], 0.05, (0, n, 2 * n))
+    fin = ho.finalize(res["wss_sum"], res["tawss_sum"], res["twssg_sum"], res["count"])
+    for name in H.FIELDS:
+        got = io_dolfin.read_checkpoint(raw / "Hemodynamic_indices", name, 0)["values"]
+        assert H.rel_l2(got, fin[name]) < 1e-10, name

@@ -8,6 +8,10 @@ name (misspelling included) and signature (``:160-161``), same command-line flag
 conventions (``AssertionError`` for missing inputs / ``save_deg``, ``RuntimeError`` for unreadable parameters, the OSI
 range assertion after the files are written, ``:366-372``).
 
+One extension of the input side: when ``Visualization_separate_domain/`` is missing the reference
+first converts the raw turtleFSI output with ``create_hdf5()`` (``:389-431``); here the raw
+``Visualization/velocity*.h5`` arrays are read in place (:mod:`vasp_b200.io_turtle`) and sliced on the GPU.
+
 What changed underneath: dolfin's per-snapshot assemble + LU + Python dof matching is replaced by the CUDA engine
 (:mod:`vasp_b200.engine`); snapshots are ``pread`` from ``u.h5`` into pinned buffers by a reader thread while the
 GPU works on the previous block; under a launcher (one process per GPU, torchrun-style ``RANK``/``WORLD_SIZE``)
@@ -25,7 +29,7 @@ from typing import Dict, Optional, Union
 
 import numpy as np
 
-from . import io_dolfin
+from . import io_dolfin, io_turtle
 from .engine import HemoEngine, pinned_empty
 from .timeshard import NcclComm, env_rank_world, plan_shard
 
@@ -119,7 +123,8 @@ class _BlockReader:
 
 def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path: Path,
                           mu_f: float, stride: int = 1, velocity_degree: int = 2,
-                          device: Optional[int] = None, block_snapshots: Optional[int] = None) -> None:
+                          device: Optional[int] = None, block_snapshots: Optional[int] = None,
+                          series=None) -> None:
     """
     Compute hemodynamic indices from velocity field (reference ``compute_hemodynamics.py:160-372``).
 
@@ -128,14 +133,17 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
         mesh_path (Path): Path to the mesh folder
         mu_f (float): Dynamic viscosity
         stride (int): Save frequency of output data
+        series: (extension) an already opened velocity series, e.g. :class:`io_turtle.TurtleVelocitySeries` over the
+            raw turtleFSI output; ``u.h5`` is not needed then and ``stride`` has been applied by whoever opened it
     """
     rank, local_rank, world = env_rank_world()
     visualization_separate_domain_folder = Path(visualization_separate_domain_folder)
     mesh_path = Path(mesh_path)
-    file_path_u = visualization_separate_domain_folder / "u.h5"
-    assert file_path_u.exists(), f"Velocity file {file_path_u} not found.  Make sure to run create_hdf5.py first."
     t_begin = time.perf_counter()
-    series = io_dolfin.VelocitySeries(file_path_u, "velocity", stride)
+    if series is None:
+        file_path_u = visualization_separate_domain_folder / "u.h5"
+        assert file_path_u.exists(), f"Velocity file {file_path_u} not found.  Make sure to run create_hdf5.py first."
+        series = io_dolfin.VelocitySeries(file_path_u, "velocity", stride)
 
     if rank == 0:
         print("--- Read the original mesh and also the refined mesh \n")
@@ -274,15 +282,44 @@ def main(argv=None) -> None:
     if parameters is None:
         raise RuntimeError("Error reading parameters from file.")
 
+    series = None
     if visualization_separate_domain_folder.exists():
         if rank == 0:
             print("--- Visualization_separate_domain folder found \n")
     else:
         if rank == 0:
             print("--- Visualization_separate_domain folder not found \n")
-        # The reference falls back to create_hdf5() here (compute_hemodynamics.py:389-431); that converter is the
-        # producer of this path's input and is not part of it.
-        raise AssertionError(f"{visualization_separate_domain_folder} not found.  Run vasp-create-hdf5 first.")
+        # The reference converts the raw turtleFSI output to u.h5 / d_solid.h5 here (create_hdf5(),
+        # compute_hemodynamics.py:389-431) and then reads u.h5 back.  Same parameters, same mesh checks, same step
+        # selection -- but the fluid-node slice of every raw array is taken on the GPU and nothing is re-written
+        # (SURVEY.md §8f-1).  The displacement file of the solid post-processing is not this path's business:
+        # vasp-create-hdf5 still makes it.
+        visualization_path = folder_path / "Visualization"
+        save_deg = parameters["save_deg"]
+        dt = parameters["dt"]
+        save_step = parameters["save_step"]
+        save_time_step = dt * save_step
+        logging.info(f"save_time_step: {save_time_step} \n")
+        fluid_domain_id = parameters["dx_f_id"]
+        solid_domain_id = parameters["dx_s_id"]
+        logging.info(f"--- Fluid domain ID: {fluid_domain_id} and Solid domain ID: {solid_domain_id} \n")
+        if args.mesh_path:
+            domain_mesh_path = Path(args.mesh_path)
+            logging.info("--- Using user-defined mesh \n")
+            assert domain_mesh_path.exists(), f"Mesh file {domain_mesh_path} not found."
+        elif save_deg == 2:
+            domain_mesh_path = folder_path / "Mesh" / "mesh_refined.h5"
+            logging.info("--- Using refined mesh \n")
+            assert domain_mesh_path.exists(), f"Mesh file {domain_mesh_path} not found."
+        else:
+            domain_mesh_path = folder_path / "Mesh" / "mesh.h5"
+            logging.info("--- Using non-refined mesh \n")
+            assert domain_mesh_path.exists(), f"Mesh file {domain_mesh_path} not found."
+        if rank == 0:
+            print(f"save_time_step: {save_time_step} \n")
+            print("--- Reading the fluid velocity straight from Visualization/velocity.h5 (no u.h5 is written) \n")
+        series = io_turtle.TurtleVelocitySeries(visualization_path, domain_mesh_path, save_time_step, args.stride,
+                                                args.start_time, args.end_time, fluid_domain_id, solid_domain_id)
 
     save_deg = parameters["save_deg"]
     if args.velocity_degree == 2:
@@ -306,7 +343,7 @@ def main(argv=None) -> None:
         assert mesh_path.exists(), f"Mesh file {mesh_path} not found."
 
     compute_hemodyanamics(visualization_separate_domain_folder, mesh_path, mu_f, args.stride,
-                          velocity_degree=args.velocity_degree, device=args.device)
+                          velocity_degree=args.velocity_degree, device=args.device, series=series)
 
 
 if __name__ == "__main__":

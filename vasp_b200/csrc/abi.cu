@@ -198,7 +198,16 @@ int vh_set_velocity_layout(vh_handle* h, int order, const double* refined_xyz, i
     VH_CHECK(h, VH_ERR_ARG, "vh_set_velocity_layout: null handle");
     VH_CUDA(cudaSetDevice(h->device));
     VH_CHECK(comp_offset && node_stride >= 1, VH_ERR_ARG, "vh_set_velocity_layout: bad layout");
-    int64_t max_slot = (n_nodes - 1) * node_stride;
+    // node_perm may be an injection into a longer vector (e.g. the fluid nodes inside a whole-domain array)
+    int64_t n_slots = n_nodes;
+    if (node_perm) {
+        n_slots = 0;
+        for (int64_t i = 0; i < n_nodes; ++i) {
+            VH_CHECK(node_perm[i] >= 0, VH_ERR_ARG, "vh_set_velocity_layout: node_perm[%lld] is negative", (long long)i);
+            if (node_perm[i] + 1 > n_slots) n_slots = node_perm[i] + 1;
+        }
+    }
+    int64_t max_slot = (n_slots - 1) * node_stride;
     for (int c = 0; c < 3; ++c) VH_CHECK(comp_offset[c] >= 0, VH_ERR_ARG, "negative component offset");
     VH_CHECK(max_slot < (1LL << 31), VH_ERR_ARG, "velocity vector too long for int32 gather slots");
     h->node_stride = node_stride;
@@ -207,7 +216,7 @@ int vh_set_velocity_layout(vh_handle* h, int order, const double* refined_xyz, i
     for (int c = 1; c < 3; ++c) top = comp_offset[c] > top ? comp_offset[c] : top;
     h->vec_len = top + max_slot + 1;  // doubles per snapshot vector that the gather can touch
     k_free_run_buffers(h);
-    return k0_build_velocity_map(h, order, refined_xyz, n_nodes, tol, node_perm);
+    return k0_build_velocity_map(h, order, refined_xyz, n_nodes, tol, node_perm, n_slots);
 }
 
 int vh_get_sizes(vh_handle* h, int64_t n[7]) {

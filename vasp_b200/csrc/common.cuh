@@ -149,7 +149,7 @@ struct vh_handle {
 // ---- K0 (k0_precompute.cu) --------------------------------------------------------------------------------------
 int k0_build_mesh(vh_handle* h, const double* xyz, int64_t nv, const int64_t* tets, int64_t nc);
 int k0_build_velocity_map(vh_handle* h, int order, const double* refined_xyz, int64_t n_nodes, double tol,
-                          const int64_t* node_perm);
+                          const int64_t* node_perm, int64_t n_slots);
 
 // ---- K1 (k1_stage.cu) ------------------------------------------------------------------------------------------------
 // W[((i * (w_ld / 32) + col / 32) * 3 + c) * 32 + col % 32] = u[col * stride_elems + comp_offset[c] + wall_slot[i]]

@@ -726,7 +726,7 @@ int k0_build_mesh(vh_handle* h, const double* xyz, int64_t nv, const int64_t* te
 }
 
 int k0_build_velocity_map(vh_handle* h, int order, const double* refined_xyz, int64_t n_nodes, double tol,
-                          const int64_t* node_perm) {
+                          const int64_t* node_perm, int64_t n_slots) {
     VH_CHECK(h->nF > 0, VH_ERR_ARG, "vh_set_velocity_layout: call vh_set_mesh first");
     VH_CHECK(order == 1 || order == 2, VH_ERR_ARG, "vh_set_velocity_layout: order must be 1 or 2");
     cudaStream_t st = h->s_compute;
@@ -798,27 +798,28 @@ int k0_build_velocity_map(vh_handle* h, int order, const double* refined_xyz, in
         VH_TRY(dev_alloc(&d_perm, n_nodes));
         VH_CUDA(cudaMemcpyAsync(d_perm, node_perm, sizeof(int64_t) * n_nodes, cudaMemcpyHostToDevice, st));
     }
+    VH_CHECK(n_slots < (1LL << 31), VH_ERR_ARG, "too many vector slots for int32");
     // wall-layer node list (ascending vector position) and the per-facet row table K2 reads the staged block with
     int32_t *d_flag = nullptr, *d_pos = nullptr, *d_cnt = nullptr;
-    VH_TRY(dev_alloc(&d_flag, n_nodes));
-    VH_TRY(dev_alloc(&d_pos, n_nodes));
+    VH_TRY(dev_alloc(&d_flag, n_slots));
+    VH_TRY(dev_alloc(&d_pos, n_slots));
     VH_TRY(dev_alloc(&d_cnt, 2));
-    VH_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int32_t) * n_nodes, st));
+    VH_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int32_t) * n_slots, st));
     VH_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int32_t) * 2, st));
     k0_mark_wall_nodes<<<nblk(ndof * nF), TPB, 0, st>>>(h->d_facet_nodes, h->d_bcell_local, h->d_facet_local, d_perm, nF,
-                                                        ndof, n_nodes, d_flag, d_cnt + 1);
+                                                        ndof, n_slots, d_flag, d_cnt + 1);
     VH_CUDA(cudaGetLastError());
-    VH_TRY(exclusive_scan(d_flag, d_pos, n_nodes, d_cnt, st));
+    VH_TRY(exclusive_scan(d_flag, d_pos, n_slots, d_cnt, st));
     int32_t cnt[2];
     VH_CUDA(cudaMemcpy(cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost));
     if (cnt[1] != 0) {
         dev_free(d_flag); dev_free(d_pos); dev_free(d_cnt); dev_free(d_perm);
-        VH_CHECK(false, VH_ERR_ARG, "vh_set_velocity_layout: node_perm has %d entries outside [0, n_nodes)", cnt[1]);
+        VH_CHECK(false, VH_ERR_ARG, "vh_set_velocity_layout: node_perm has %d entries outside the vector", cnt[1]);
     }
     h->nWn = cnt[0];
     h->nWn_pad = (h->nWn + 31) / 32 * 32;
     VH_TRY(dev_alloc(&h->d_wall_slot, h->nWn_pad));
-    k0_wall_slots<<<nblk(n_nodes), TPB, 0, st>>>(d_flag, d_pos, n_nodes, h->node_stride, h->nWn, h->nWn_pad,
+    k0_wall_slots<<<nblk(n_slots), TPB, 0, st>>>(d_flag, d_pos, n_slots, h->node_stride, h->nWn, h->nWn_pad,
                                                  h->d_wall_slot);
     k0_rows<<<nblk(ndof * nF), TPB, 0, st>>>(h->d_facet_nodes, h->d_bcell_local, h->d_facet_local, d_perm, d_pos, nF,
                                              ndof, h->d_row);

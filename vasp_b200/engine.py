@@ -94,13 +94,14 @@ class HemoEngine:
             comp_offset = (0, n_nodes, 2 * n_nodes)
         if node_perm is not None:
             node_perm = np.ascontiguousarray(node_perm, dtype=np.int64)
-            if node_perm.shape != (n_nodes,):
-                raise ValueError("node_perm must have one entry per velocity node")
+            if node_perm.shape != (n_nodes,) or (n_nodes and node_perm.min() < 0):
+                raise ValueError("node_perm must have one non-negative entry per velocity node")
         off = (C.c_int64 * 3)(*[int(x) for x in comp_offset])
         check(self._lib.vh_set_velocity_layout(self._h, int(order), _ptr(refined_xyz), int(n_nodes), float(tol),
                                                _ptr(node_perm), off, int(node_stride)))
         self.order = int(order)
-        self.vec_len = max(comp_offset) + (n_nodes - 1) * node_stride + 1
+        n_slots = n_nodes if node_perm is None else int(node_perm.max()) + 1  # node_perm may point into a longer vector
+        self.vec_len = max(comp_offset) + (n_slots - 1) * node_stride + 1
         self._refresh_sizes()
 
     def _refresh_sizes(self) -> None:
