@@ -284,6 +284,7 @@ int vh_begin(vh_handle* h, double mu, double dt) {
     // no memsets on the hot path: the first K3 of the loop overwrites the sums instead of adding to them, and
     // tau_last is only read after a launch has written it
     h->sums_pending_zero = true;
+    h->out5_count = -1;
     h->sums_reduced = false;
     h->loop_parity ^= 1;  // alternate halves of the peer-visible block (see common.cuh)
     h->d_sums = h->d_sums_block + (int64_t)h->loop_parity * h->sum_stride;
@@ -500,6 +501,7 @@ int vh_set_sums(vh_handle* h, const double* sums, int64_t count) {
     VH_CHECK(sums, VH_ERR_ARG, "vh_set_sums: null sums");
     h->sums_pending_zero = false;
     h->sums_reduced = false;
+    h->out5_count = -1;
     VH_CUDA(cudaStreamSynchronize(h->s_compute));
     VH_CUDA(cudaMemcpy(h->d_sums, sums, sizeof(double) * VH_NSUM * h->nF, cudaMemcpyHostToDevice));
     h->count = count;
@@ -530,7 +532,8 @@ int vh_finalize(vh_handle* h, int64_t n_total, double* tawss, double* osi, doubl
     VH_TRY(check_ready(h, "vh_finalize"));
     VH_CHECK(n_total > 0, VH_ERR_ARG, "vh_finalize: n_total must be positive");
     VH_TRY(settle_sums(h));
-    VH_TRY(k4_finalize(h, n_total, h->d_out5));
+    // the fold of the last launch already evaluated the indices for the snapshots it had seen
+    if (h->out5_count != n_total) VH_TRY(k4_finalize(h, n_total, h->d_out5));
     double* const outs[5] = {tawss, osi, rrt, ecap, twssg};
     // with no host outputs the call stays asynchronous (device-resident timing); results remain in HBM
     return export_out5(h, outs);
@@ -709,6 +712,7 @@ int vh_nccl_allreduce_sums(vh_handle* h) {
     VH_NCCL(g_nccl.AllReduce(h->d_sums, h->d_sums, (size_t)(n + 1), ncclDouble, ncclSum, (ncclComm_t)h->nccl_comm,
                              h->s_compute));
     h->count_on_device = true;
+    h->out5_count = -1;  // the sums are global now
     h->launches += 1;
     return VH_OK;
 }
@@ -817,6 +821,7 @@ int vh_peer_reduce_finalize(vh_handle* h, int64_t n_total, double* tawss, double
     VH_TRY(k4_peer_reduce_finalize(h, pb, half_off, flags_off, h->peer_epoch, n_total, h->d_sums_red, h->d_out5));
     h->sums_reduced = true;
     h->count_on_device = true;
+    h->out5_count = -1;  // d_out5 holds the global indices; the local count no longer describes it
     double* const outs[5] = {tawss, osi, rrt, ecap, twssg};
     return export_out5(h, outs);
 }

@@ -116,6 +116,7 @@ struct vh_handle {
     int tau_cur = 0;
     double* d_out5 = nullptr;      // [5][3*nF] TAWSS, OSI, RRT, ECAP, TWSSG
     double* h_out5 = nullptr;      // pinned staging copy of d_out5 for the D2H export
+    int64_t out5_count = -1;       // snapshot count d_out5 was evaluated for by the last fold (-1: stale)
     std::vector<cudaEvent_t> batch_events;  // timing events of vh_push_snapshots, reused across calls
     double* d_part = nullptr;      // [groups][15][nF] partial sums of one launch
     int64_t part_cap = 0;          // capacity in groups

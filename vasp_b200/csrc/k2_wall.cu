@@ -238,6 +238,18 @@ __device__ __forceinline__ void store_partials(double (&acc)[VH_NSUM], double* p
     }
 }
 
+// compute_hemodynamics.py:326-346 for one boundary dof: v = {sum tau_x, sum tau_y, sum tau_z, sum |tau|, sum P(|dtau/dt|)}
+__device__ __forceinline__ void hemo_indices(const double (&v)[5], double count, double (&out)[5]) {
+    const double mean_mag = norm3(v[0] / count, v[1] / count, v[2] / count);
+    const double ta = v[3] / count;
+    const double o = 0.5 * (1.0 - mean_mag / ta);
+    out[0] = ta;
+    out[1] = o;
+    out[2] = 1.0 / mean_mag;
+    out[3] = o / ta;
+    out[4] = v[4] / count;
+}
+
 // One warp = one facet x one time segment; the 32 lanes are the 32 columns of a tile of the staged block.
 // P2 data, facets whose cell owns no other exterior facet (work[0, multi_start)).
 __device__ __forceinline__ void k2_body_p2(const K2Args& a, const K2Seg& sg, int bx, int y, double* k2_smem) {
@@ -563,8 +575,7 @@ __device__ __forceinline__ void k2_body_flat2(const K2Args& a, const K2Seg& sg, 
         double* p = sg.part + (int64_t)y * VH_NSUM * T.n_work + w;
 #pragma unroll
         for (int i = 0; i < VH_NSUM; ++i) p[(int64_t)i * T.n_work] = i < 9 ? acc[i % 3] : i < 12 ? acc[3] : acc[4] * s;
-    }
-}
+    }}
 
 template <int ORDER>
 __global__ void __launch_bounds__(32 * K2_WARPS, 3) k2_wall(const K2Args a) {
@@ -582,35 +593,49 @@ __global__ void __launch_bounds__(32 * K2_WARPS, 3) k2_wall(const K2Args a) {
 }
 
 // sums[i][f] (+)= sum over the segments of part[q][i][w], f = work[w], in fixed order, plus the TWSSG terms of the
-// segment boundaries, P(|tau_first(s) - tau_last(s - 1)| / dt), which no segment could form on its own.  The
-// single-facet and the multi-facet launches have their own segment counts and buffers.
-__global__ void k3_fold(double* __restrict__ sums, const double* __restrict__ part_s, const double* __restrict__ bnd_s,
-                        int gy_s, const double* __restrict__ part_m, const double* __restrict__ bnd_m, int gy_m,
-                        const int32_t* __restrict__ work, int64_t n_work, int64_t multi_start, int64_t nF,
-                        double inv_dt, int overwrite) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= VH_NSUM * n_work) return;
-    const int64_t w = idx % n_work;
-    const int i = (int)(idx / n_work);
-    const int32_t f = work[w];
-    if (f < 0) return;
-    const bool multi = w >= multi_start;
-    const double* part = (multi ? part_m : part_s) + (int64_t)i * n_work + w;
-    const double* bnd = (multi ? bnd_m : bnd_s) + w;
-    const int gq = multi ? gy_m : gy_s;
-    double t = overwrite ? 0.0 : sums[(int64_t)i * nF + f];  // first launch of a time loop: no memset needed
-    for (int q = 0; q < gq; ++q) {
-        t += part[(int64_t)q * VH_NSUM * n_work];
-        if (i >= 12 && q > 0) {  // the three TWSSG rows each evaluate the boundary projection and keep their entry
-            double dw[9], p[3];
+// segment boundaries, P(|tau_first(s) - tau_last(s - 1)| / dt), which no segment could form on its own; then the final
+// formulas (:326-346) for the snapshots seen so far -- vh_finalize reuses them when the count matches, so a step on the
+// hot path is three launches (K1, K2, K3).  A block takes 16 work items: thread (row i, item) folds one sum row
+// (16 consecutive items per row: 128-byte runs), the rows meet in shared memory, 48 threads evaluate the indices.
+// The single-facet and the multi-facet paths have their own segment counts and buffers.
+constexpr int K3_ITEMS = 16;
+__global__ void __launch_bounds__(16 * K3_ITEMS)
+    k3_fold(double* __restrict__ sums, const double* __restrict__ part_s, const double* __restrict__ bnd_s, int gy_s,
+            const double* __restrict__ part_m, const double* __restrict__ bnd_m, int gy_m,
+            const int32_t* __restrict__ work, int64_t n_work, int64_t multi_start, int64_t nF, double inv_dt,
+            int overwrite, double count, double* __restrict__ out5) {
+    __shared__ double rows[VH_NSUM][K3_ITEMS];
+    const int wl = threadIdx.x % K3_ITEMS, i = threadIdx.x / K3_ITEMS;  // i = 15: idle row
+    const int64_t w = (int64_t)blockIdx.x * K3_ITEMS + wl;
+    const int32_t f = w < n_work ? work[w] : -1;
+    if (f >= 0 && i < VH_NSUM) {
+        const bool multi = w >= multi_start;
+        const double* part = (multi ? part_m : part_s) + (int64_t)i * n_work + w;
+        const double* bnd = (multi ? bnd_m : bnd_s) + w;
+        const int gq = multi ? gy_m : gy_s;
+        double t = overwrite ? 0.0 : sums[(int64_t)i * nF + f];  // first launch of a time loop: no memset needed
+        for (int q = 0; q < gq; ++q) {
+            t += part[(int64_t)q * VH_NSUM * n_work];
+            if (i >= 12 && q > 0) {  // the three TWSSG rows each evaluate the boundary projection and keep their entry
+                double dw[9], p[3];
 #pragma unroll
-            for (int c = 0; c < 9; ++c)
-                dw[c] = bnd[((int64_t)(2 * q) * 9 + c) * n_work] - bnd[((int64_t)(2 * q - 1) * 9 + c) * n_work];
-            twssg_project(dw, p);
-            t += (i == 12 ? p[0] : i == 13 ? p[1] : p[2]) * fabs(inv_dt);
+                for (int c = 0; c < 9; ++c)
+                    dw[c] = bnd[((int64_t)(2 * q) * 9 + c) * n_work] - bnd[((int64_t)(2 * q - 1) * 9 + c) * n_work];
+                twssg_project(dw, p);
+                t += (i == 12 ? p[0] : i == 13 ? p[1] : p[2]) * fabs(inv_dt);
+            }
         }
+        sums[(int64_t)i * nF + f] = t;
+        rows[i][wl] = t;
     }
-    sums[(int64_t)i * nF + f] = t;
+    __syncthreads();
+    if (f >= 0 && i < 3) {  // boundary dof j = i of facet f
+        const double v[5] = {rows[3 * i][wl], rows[3 * i + 1][wl], rows[3 * i + 2][wl], rows[9 + i][wl], rows[12 + i][wl]};
+        double o[5];
+        hemo_indices(v, count, o);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) out5[(int64_t)k * 3 * nF + 3 * f + i] = o[k];
+    }
 }
 
 // compute_hemodynamics.py:326-346
@@ -621,18 +646,17 @@ __global__ void k4_indices(const double* __restrict__ sums, int64_t nF, double c
     if (i >= 3 * nF) return;
     int64_t f = i % nF;
     int j = (int)(i / nF);
-    double mx = sums[(int64_t)(3 * j + 0) * nF + f] / count;
-    double my = sums[(int64_t)(3 * j + 1) * nF + f] / count;
-    double mz = sums[(int64_t)(3 * j + 2) * nF + f] / count;
-    double mean_mag = norm3(mx, my, mz);
-    double ta = sums[(int64_t)(9 + j) * nF + f] / count;
-    double o = 0.5 * (1.0 - mean_mag / ta);
-    int64_t q = 3 * f + j;
-    tawss[q] = ta;
-    osi[q] = o;
-    rrt[q] = 1.0 / mean_mag;
-    ecap[q] = o / ta;
-    twssg[q] = sums[(int64_t)(12 + j) * nF + f] / count;
+    const double v[5] = {sums[(int64_t)(3 * j + 0) * nF + f], sums[(int64_t)(3 * j + 1) * nF + f],
+                         sums[(int64_t)(3 * j + 2) * nF + f], sums[(int64_t)(9 + j) * nF + f],
+                         sums[(int64_t)(12 + j) * nF + f]};
+    double o[5];
+    hemo_indices(v, count, o);
+    const int64_t q = 3 * f + j;
+    tawss[q] = o[0];
+    osi[q] = o[1];
+    rrt[q] = o[2];
+    ecap[q] = o[3];
+    twssg[q] = o[4];
 }
 
 // ---- peer-memory reduction (one process per GPU, memory mapped with CUDA IPC) ------------------------------------------
@@ -755,6 +779,7 @@ int k_free_run_buffers(vh_handle* h) {
     if (h->d_tau_last[0]) cudaFree(h->d_tau_last[0]);
     if (h->d_tau_last[1]) cudaFree(h->d_tau_last[1]);
     if (h->d_part) cudaFree(h->d_part);
+    h->out5_count = -1;
     if (h->d_out5) cudaFree(h->d_out5);
     if (h->h_out5) cudaFreeHost(h->h_out5);
     h->h_out5 = nullptr;
@@ -910,15 +935,17 @@ int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_el
             cudaEventRecord(h->prof_pool[h->prof_used + 2], h->s_compute);
             h->prof_used += 3;
         }
-        k3_fold<<<(unsigned)((VH_NSUM * h->n_work + 127) / 128), 128, 0, h->s_compute>>>(
+        k3_fold<<<(unsigned)((h->n_work + K3_ITEMS - 1) / K3_ITEMS), 16 * K3_ITEMS, 0, h->s_compute>>>(
             h->d_sums, a.single.part, a.single.bnd, a.single.gy, a.multi.part, a.multi.bnd, a.multi.gy, h->d_work,
-            h->n_work, h->multi_start, nF, a.inv_dt, h->sums_pending_zero ? 1 : 0);
-        h->sums_pending_zero = false;
+            h->n_work, h->multi_start, nF, a.inv_dt, h->sums_pending_zero ? 1 : 0, (double)(h->count + pos + nb),
+            h->d_out5);
         VH_CUDA(cudaGetLastError());
         h->launches += 1;
+        h->sums_pending_zero = false;
         pos += nb;
     }
     h->count += n_snap;
+    h->out5_count = h->count;  // the last fold left the indices of exactly these snapshots in d_out5
     h->have_tau_last = true;
     return VH_OK;
 }
