@@ -63,9 +63,10 @@ int nccl_load() {
 int ensure_run_buffers(vh_handle* h) {
     const int64_t nF = h->nF;
     if (!h->d_sums_block) {
-        // two halves of (15 nF sums + the snapshot count), then the arrival counters of the peer reduction
+        // two halves of (15 nF sums + the snapshot count), then the arrival counters of the peer reduction and one
+        // word that a reduction sets when a peer never arrived (bounded wait, see k4_peer_indices)
         h->sum_stride = (VH_NSUM * nF + 1 + 15) / 16 * 16;
-        const size_t bytes = sizeof(double) * (2 * h->sum_stride + VH_MAX_PEERS);
+        const size_t bytes = sizeof(double) * (2 * h->sum_stride + VH_MAX_PEERS + 1);
         VH_CUDA(cudaMalloc(&h->d_sums_block, bytes));
         VH_CUDA(cudaMemset(h->d_sums_block, 0, bytes));
         VH_CUDA(cudaMalloc(&h->d_sums_red, sizeof(double) * (VH_NSUM * nF + 1)));
@@ -539,12 +540,27 @@ int vh_finalize(vh_handle* h, int64_t n_total, double* tawss, double* osi, doubl
     return export_out5(h, outs);
 }
 
+// A fused peer reduction whose wait ran out marks the word behind the arrival counters; every call that synchronises
+// after one looks at it, so a lost rank ends in an error on the survivors instead of a hung GPU.
+static int peer_check(vh_handle* h) {
+    if (!h->peer_unchecked) return VH_OK;
+    uint64_t lost = 0;
+    VH_CUDA(cudaMemcpyAsync(&lost, h->d_sums_block + 2 * h->sum_stride + VH_MAX_PEERS, sizeof(lost),
+                            cudaMemcpyDeviceToHost, h->s_compute));
+    VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    h->peer_unchecked = false;
+    VH_CHECK(lost == 0, VH_ERR_NCCL,
+             "vh_peer_reduce_finalize: rank %d never signalled epoch %llu within %.0f s (results are invalid)",
+             (int)(lost - 1), (unsigned long long)h->peer_epoch, VH_PEER_WAIT_NS * 1e-9);
+    return VH_OK;
+}
+
 int vh_sync(vh_handle* h) {
     VH_CHECK(h, VH_ERR_ARG, "vh_sync: null handle");
     VH_CUDA(cudaSetDevice(h->device));
     VH_CUDA(cudaStreamSynchronize(h->s_copy));
     VH_CUDA(cudaStreamSynchronize(h->s_compute));
-    return VH_OK;
+    return peer_check(h);
 }
 
 int vh_get_timers(vh_handle* h, double* kernel_ms, double* h2d_ms, int64_t* launches) {
@@ -822,8 +838,11 @@ int vh_peer_reduce_finalize(vh_handle* h, int64_t n_total, double* tawss, double
     h->sums_reduced = true;
     h->count_on_device = true;
     h->out5_count = -1;  // d_out5 holds the global indices; the local count no longer describes it
+    h->peer_unchecked = true;
     double* const outs[5] = {tawss, osi, rrt, ecap, twssg};
-    return export_out5(h, outs);
+    VH_TRY(export_out5(h, outs));
+    if (tawss || osi || rrt || ecap || twssg) return peer_check(h);  // export_out5 synchronised
+    return VH_OK;
 }
 
 int vh_nccl_destroy(vh_handle* h) {

@@ -38,6 +38,7 @@ void vh_set_error(const char* fmt, ...);
 constexpr int VH_NSUM = 15;
 constexpr int VH_MAX_CONTRIB = 4;  // a tet has at most 4 exterior facets
 constexpr int VH_MAX_PEERS = 8;     // GPUs of one NVSwitch node
+constexpr unsigned long long VH_PEER_WAIT_NS = 60ull * 1000000000ull;  // longest a fused reduction waits for a peer
 constexpr int VH_MROW = 10;        // row length of the multi-facet operator: 9 outputs padded for 16-byte loads
 
 // Per-facet constants in HBM, all SoA over facets (row r of an array with R rows: ptr[r * nF + f]).
@@ -111,6 +112,7 @@ struct vh_handle {
     bool sums_reduced = false;     // vh_get_sums reads d_sums_red
     bool peer_ready = false;
     uint64_t peer_epoch = 0;
+    bool peer_unchecked = false;   // a fused reduction was enqueued and its "peer lost" word not looked at yet
     double* peer_block[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double* d_tau_last[2] = {nullptr, nullptr};  // [9][nF], ping-pong (read by first chunk, written by last)
     int tau_cur = 0;

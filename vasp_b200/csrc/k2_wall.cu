@@ -668,6 +668,11 @@ __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
 __device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ double ld_peer(const double* p) {
     // system-scope relaxed load: goes to the owner's memory (peer lines are never in the local L2, and the local L1
     // holds nothing of them at this point of a fresh kernel), and -- unlike volatile -- loads may overlap
@@ -694,8 +699,14 @@ __global__ void k4_peer_indices(PeerBlocks pb, int world, int rank, int64_t half
                                 double* __restrict__ osi, double* __restrict__ rrt, double* __restrict__ ecap,
                                 double* __restrict__ twssg) {
     if ((int)threadIdx.x < world) {
-        const uint64_t* flags = reinterpret_cast<const uint64_t*>(pb.block[rank] + flags_off);  // local memory
+        uint64_t* flags = reinterpret_cast<uint64_t*>(const_cast<double*>(pb.block[rank]) + flags_off);  // local memory
+        const uint64_t t0 = global_ns();
         while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
+            if (global_ns() - t0 > VH_PEER_WAIT_NS) {  // a rank died: give up, tell the host which one
+                flags[VH_MAX_PEERS] = threadIdx.x + 1;
+                break;
+            }
+            __nanosleep(200);
         }
     }
     __syncthreads();

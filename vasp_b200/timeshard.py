@@ -173,6 +173,10 @@ class NcclComm:
     def reduce_finalize(self, n_total: int, host: bool = True):
         """Global TAWSS/OSI/RRT/ECAP/TWSSG on every rank: fused peer reduction if mapped, else all-reduce + K4."""
         if self.fused:
+            if host:
+                # ranks may arrive minutes apart (file I/O); wait on the host so that the kernel's bounded wait
+                # (VH_PEER_WAIT_NS) only ever covers stream skew
+                self.engine.barrier()
             return self.engine.peer_reduce_finalize(n_total, host=host)
         self.engine.allreduce_sums()
         if host:
