@@ -138,6 +138,7 @@ int vh_create(int device, vh_handle** out) {
     cudaDeviceProp prop;
     VH_CUDA(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("VASP_B200_PDL")) h->pdl = atoi(e);
     VH_CUDA(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
     VH_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
     VH_CUDA(cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking));

@@ -38,6 +38,29 @@ void vh_set_error(const char* fmt, ...);
 constexpr int VH_NSUM = 15;
 constexpr int VH_MAX_CONTRIB = 4;  // a tet has at most 4 exterior facets
 constexpr int VH_MAX_PEERS = 8;     // GPUs of one NVSwitch node
+// Programmatic dependent launch (sm_90+): a kernel launched with vh_launch_pdl may start while its predecessor in the
+// stream drains; it must not touch anything the predecessor (or, transitively, an earlier kernel) writes or reads-
+// then-overwrites before pdl_wait().  Every thread of every hot kernel executes pdl_wait(), so completion is transitive
+// along the stream.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t vh_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                 Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
 constexpr unsigned long long VH_PEER_WAIT_NS = 60ull * 1000000000ull;  // longest a fused reduction waits for a peer
 constexpr int VH_MROW = 10;        // row length of the multi-facet operator: 9 outputs padded for 16-byte loads
 
@@ -112,6 +135,9 @@ struct vh_handle {
     bool sums_reduced = false;     // vh_get_sums reads d_sums_red
     bool peer_ready = false;
     uint64_t peer_epoch = 0;
+    // programmatic stream serialization per kernel: bit 0 K1, bit 1 K2, bit 2 K3 (VASP_B200_PDL).  Measured (profiles/
+    // r1pdl): K1 + K2 is the best mask (55.8 us per headline step against 64 without); adding K3 costs 30 us on P2.
+    int pdl = 3;
     bool peer_unchecked = false;   // a fused reduction was enqueued and its "peer lost" word not looked at yet
     double* peer_block[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double* d_tau_last[2] = {nullptr, nullptr};  // [9][nF], ping-pong (read by first chunk, written by last)

@@ -50,6 +50,9 @@ __global__ void __launch_bounds__(TILE* ROWS)
             v[r][0] = v[r][1] = v[r][2] = 0.0;
         }
     }
+    // the loads above touch only the input vectors; W is still being read by the previous launch's K2 until here
+    pdl_wait();
+    pdl_launch_dependents();
 #pragma unroll
     for (int r = 0; r < TILE / ROWS; ++r) {
         tile[0][ty + ROWS * r][tx] = v[r][0];
@@ -76,9 +79,9 @@ int k1_launch(vh_handle* h, const double* d_u, int64_t ncol, int64_t stride_elem
     const int64_t gy = (ncol + 2 * TILE - 1) / (2 * TILE) * 2;  // zero-filled up to whole 64-column passes of K2
     VH_CHECK(gy <= 65535, VH_ERR_ARG, "k1_launch: too many snapshots in one block");
     dim3 grid((unsigned)(h->nWn_pad / TILE), (unsigned)gy), block(TILE, ROWS);
-    k1_stage<<<grid, block, 0, h->s_compute>>>(d_u, stride_elems, (int)ncol, h->d_wall_slot, h->comp_offset[0],
-                                               h->comp_offset[1], h->comp_offset[2], h->d_W, h->w_ld / TILE);
-    VH_CUDA(cudaGetLastError());
+    VH_CUDA(vh_launch_pdl(k1_stage, grid, block, 0, h->s_compute, (h->pdl & 1) && !h->profile, d_u, stride_elems, (int)ncol,
+                          (const int32_t*)h->d_wall_slot, h->comp_offset[0], h->comp_offset[1], h->comp_offset[2],
+                          h->d_W, h->w_ld / TILE));
     h->launches += 1;
     return VH_OK;
 }

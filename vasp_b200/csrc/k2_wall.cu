@@ -580,6 +580,8 @@ __device__ __forceinline__ void k2_body_flat2(const K2Args& a, const K2Seg& sg, 
 template <int ORDER>
 __global__ void __launch_bounds__(32 * K2_WARPS, 3) k2_wall(const K2Args a) {
     extern __shared__ __align__(16) double k2_smem[];
+    pdl_wait();  // W comes from the K1 just before; part/bnd were read by the K3 before that
+    pdl_launch_dependents();
     const int nb_multi = a.multi.gx * a.multi.gy;
     if ((int)blockIdx.x < nb_multi) {
         k2_body_multi2<ORDER>(a, a.multi, blockIdx.x % a.multi.gx, blockIdx.x / a.multi.gx, k2_smem);
@@ -607,7 +609,9 @@ __global__ void __launch_bounds__(16 * K3_ITEMS)
     __shared__ double rows[VH_NSUM][K3_ITEMS];
     const int wl = threadIdx.x % K3_ITEMS, i = threadIdx.x / K3_ITEMS;  // i = 15: idle row
     const int64_t w = (int64_t)blockIdx.x * K3_ITEMS + wl;
-    const int32_t f = w < n_work ? work[w] : -1;
+    const int32_t f = w < n_work ? work[w] : -1;  // K0's table: older than any kernel in flight
+    pdl_wait();
+    pdl_launch_dependents();
     if (f >= 0 && i < VH_NSUM) {
         const bool multi = w >= multi_start;
         const double* part = (multi ? part_m : part_s) + (int64_t)i * n_work + w;
@@ -858,7 +862,7 @@ SegPlan plan_segments(int64_t ncol, int64_t pass_cols, int64_t n_items, int64_t 
 }
 
 template <int ORDER>
-int launch_k2(const K2Args& a, cudaStream_t st) {
+int launch_k2(const K2Args& a, cudaStream_t st, bool pdl) {
     using L = K2Launch<ORDER>;
     static bool configured = false;  // per instantiation
     if (!configured && L::SMEM_BYTES > 0) {
@@ -868,8 +872,7 @@ int launch_k2(const K2Args& a, cudaStream_t st) {
         configured = true;
     }
     const unsigned blocks = (unsigned)(a.multi.gx * a.multi.gy + a.single.gx * a.single.gy);
-    k2_wall<ORDER><<<blocks, 32 * K2_WARPS, L::SMEM_BYTES, st>>>(a);
-    VH_CUDA(cudaGetLastError());
+    VH_CUDA(vh_launch_pdl(k2_wall<ORDER>, dim3(blocks), dim3(32 * K2_WARPS), L::SMEM_BYTES, st, pdl, a));
     return VH_OK;
 }
 
@@ -913,6 +916,7 @@ int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_el
             h->part_cap = groups;
         }
         const bool prof = h->profile && h->prof_used + 3 <= h->prof_pool.size();
+        const int pdl = h->profile ? 0 : h->pdl;  // events between the kernels would serialise them anyway
         if (prof) cudaEventRecord(h->prof_pool[h->prof_used], h->s_compute);
         VH_TRY(k1_launch(h, d_u + (pos - halo) * stride_elems, ncol, stride_elems));
         if (prof) cudaEventRecord(h->prof_pool[h->prof_used + 1], h->s_compute);
@@ -938,19 +942,19 @@ int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_el
         a.mu = h->mu;
         a.inv_dt = 1.0 / h->dt;
         if (h->order == 2)
-            VH_TRY(launch_k2<2>(a, h->s_compute));
+            VH_TRY(launch_k2<2>(a, h->s_compute, (pdl & 2) != 0));
         else
-            VH_TRY(launch_k2<1>(a, h->s_compute));
+            VH_TRY(launch_k2<1>(a, h->s_compute, (pdl & 2) != 0));
         h->launches += 1;
         if (prof) {
             cudaEventRecord(h->prof_pool[h->prof_used + 2], h->s_compute);
             h->prof_used += 3;
         }
-        k3_fold<<<(unsigned)((h->n_work + K3_ITEMS - 1) / K3_ITEMS), 16 * K3_ITEMS, 0, h->s_compute>>>(
-            h->d_sums, a.single.part, a.single.bnd, a.single.gy, a.multi.part, a.multi.bnd, a.multi.gy, h->d_work,
-            h->n_work, h->multi_start, nF, a.inv_dt, h->sums_pending_zero ? 1 : 0, (double)(h->count + pos + nb),
-            h->d_out5);
-        VH_CUDA(cudaGetLastError());
+        VH_CUDA(vh_launch_pdl(k3_fold, dim3((unsigned)((h->n_work + K3_ITEMS - 1) / K3_ITEMS)), dim3(16 * K3_ITEMS), 0,
+                              h->s_compute, (pdl & 4) != 0, h->d_sums, (const double*)a.single.part, (const double*)a.single.bnd,
+                              a.single.gy, (const double*)a.multi.part, (const double*)a.multi.bnd, a.multi.gy,
+                              (const int32_t*)h->d_work, h->n_work, h->multi_start, nF, a.inv_dt,
+                              h->sums_pending_zero ? 1 : 0, (double)(h->count + pos + nb), h->d_out5));
         h->launches += 1;
         h->sums_pending_zero = false;
         pos += nb;
