@@ -234,11 +234,15 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     for _ in range(args.warmup):
         step_resident()
     eng.sync()
-    launches0 = eng.timers()["launches"]
-    if comm:
-        comm.barrier()
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank) as clk:  # NVML starts before the barrier: its set-up time differs between ranks
         eng.sync()
+        if comm:
+            # Ranks leave a host barrier tens of us apart, which is not small against K steps of ~60 us.  One untimed
+            # step after the barrier lines the GPUs up on the device (its cross-GPU reduction ends on every rank when
+            # the last rank arrives); the start event is recorded on the stream right behind it.
+            comm.barrier()
+            step_resident()
+        launches0 = eng.timers()["launches"]
         eng.timer_start()
         for _ in range(args.steps):
             step_resident()
@@ -247,10 +251,12 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         # Same K steps once more with CUDA events between the kernels (per-launch K1/K2 durations for the roofline).
         # The events sit between dependent launches, so this pass runs without programmatic dependent launch and is a
         # few us per step slower than the pass above; `value` comes from the pass above.
-        if comm:
-            comm.barrier()
         eng.set_profile(True)
         eng.sync()
+        if comm:
+            comm.barrier()
+            step_resident()
+            eng.kernel_profile()  # drop the aligning step's events
         eng.timer_start()
         for _ in range(args.steps):
             step_resident()
@@ -385,7 +391,7 @@ def cpu_baseline(wl, n_snap: int):
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="stenosis_p1")

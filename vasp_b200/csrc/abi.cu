@@ -834,7 +834,6 @@ int vh_peer_reduce_finalize(vh_handle* h, int64_t n_total, double* tawss, double
     for (int q = 0; q < VH_MAX_PEERS; ++q) pb.block[q] = h->peer_block[q];
     const int64_t half_off = (int64_t)h->loop_parity * h->sum_stride, flags_off = 2 * h->sum_stride;
     h->peer_epoch += 1;
-    VH_TRY(k4_peer_signal(h, pb, flags_off, h->peer_epoch));
     VH_TRY(k4_peer_reduce_finalize(h, pb, half_off, flags_off, h->peer_epoch, n_total, h->d_sums_red, h->d_out5));
     h->sums_reduced = true;
     h->count_on_device = true;

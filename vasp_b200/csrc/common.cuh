@@ -137,7 +137,7 @@ struct vh_handle {
     uint64_t peer_epoch = 0;
     // programmatic stream serialization per kernel: bit 0 K1, bit 1 K2, bit 2 K3 (VASP_B200_PDL).  Measured (profiles/
     // r1pdl): K1 + K2 is the best mask (55.8 us per headline step against 64 without); adding K3 costs 30 us on P2.
-    int pdl = 3;
+    int pdl = 11;                  // bit 3: the fused peer reduction after K3 (2 GPUs, headline: 72.4 -> 70.3 us per step)
     bool peer_unchecked = false;   // a fused reduction was enqueued and its "peer lost" word not looked at yet
     double* peer_block[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double* d_tau_last[2] = {nullptr, nullptr};  // [9][nF], ping-pong (read by first chunk, written by last)
@@ -196,7 +196,6 @@ int k4_finalize(vh_handle* h, int64_t n_total, double* d_out5);  // d_out5: 5 ar
 struct PeerBlocks {
     const double* block[VH_MAX_PEERS];
 };
-int k4_peer_signal(vh_handle* h, const PeerBlocks& pb, int64_t flags_off, uint64_t epoch);
 int k4_peer_reduce_finalize(vh_handle* h, const PeerBlocks& pb, int64_t half_off, int64_t flags_off, uint64_t epoch,
                             int64_t n_total, double* d_red, double* d_out5);
 int k_free_run_buffers(vh_handle* h);

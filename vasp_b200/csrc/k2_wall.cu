@@ -685,23 +685,24 @@ __device__ __forceinline__ double ld_peer(const double* p) {
     return v;
 }
 
-// thread q tells rank q "rank `rank` has finished epoch `epoch`": everything this GPU wrote before (K3's sums) is
-// made visible system-wide first
-__global__ void k_peer_signal(PeerBlocks pb, int world, int rank, int64_t flags_off, uint64_t epoch, double* count_slot,
-                              double count) {
-    if (threadIdx.x == 0) *count_slot = count;  // the snapshot count rides behind the sums
-    __syncthreads();
-    if ((int)threadIdx.x >= world) return;
-    __threadfence_system();
-    uint64_t* flags = reinterpret_cast<uint64_t*>(const_cast<double*>(pb.block[threadIdx.x]) + flags_off);
-    st_release_sys(flags + rank, epoch);
-}
-
 // compute_hemodynamics.py:326-346 on sums that are still spread over the GPUs of the node
 __global__ void k4_peer_indices(PeerBlocks pb, int world, int rank, int64_t half_off, int64_t flags_off, uint64_t epoch,
                                 int64_t nF, double count, double* __restrict__ red, double* __restrict__ tawss,
                                 double* __restrict__ osi, double* __restrict__ rrt, double* __restrict__ ecap,
-                                double* __restrict__ twssg) {
+                                double* __restrict__ twssg, double* count_slot, double my_count) {
+    pdl_wait();  // K3 has folded this rank's sums
+    // Block 0 first tells every rank "rank `rank` has finished epoch `epoch`": thread q stores the epoch into rank q's
+    // arrival counter after a system-scope fence, so everything this GPU wrote before (K3's sums, the snapshot count
+    // that rides behind them) is visible to a peer that has seen the counter.
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) *count_slot = my_count;
+        __syncthreads();
+        if ((int)threadIdx.x < world) {
+            __threadfence_system();
+            uint64_t* peer_flags = reinterpret_cast<uint64_t*>(const_cast<double*>(pb.block[threadIdx.x]) + flags_off);
+            st_release_sys(peer_flags + rank, epoch);
+        }
+    }
     if ((int)threadIdx.x < world) {
         uint64_t* flags = reinterpret_cast<uint64_t*>(const_cast<double*>(pb.block[rank]) + flags_off);  // local memory
         const uint64_t t0 = global_ns();
@@ -710,10 +711,11 @@ __global__ void k4_peer_indices(PeerBlocks pb, int world, int rank, int64_t half
                 flags[VH_MAX_PEERS] = threadIdx.x + 1;
                 break;
             }
-            __nanosleep(200);
+            __nanosleep(100);
         }
     }
     __syncthreads();
+    pdl_launch_dependents();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {  // snapshot count
         double t = 0.0;
@@ -753,21 +755,14 @@ __global__ void k4_peer_indices(PeerBlocks pb, int world, int rank, int64_t half
 
 }  // namespace
 
-int k4_peer_signal(vh_handle* h, const PeerBlocks& pb, int64_t flags_off, uint64_t epoch) {
-    k_peer_signal<<<1, 32, 0, h->s_compute>>>(pb, h->world, h->rank, flags_off, epoch, h->d_sums + VH_NSUM * h->nF,
-                                              (double)h->count);
-    VH_CUDA(cudaGetLastError());
-    h->launches += 1;
-    return VH_OK;
-}
-
 int k4_peer_reduce_finalize(vh_handle* h, const PeerBlocks& pb, int64_t half_off, int64_t flags_off, uint64_t epoch,
                             int64_t n_total, double* d_red, double* d_out5) {
     const int64_t nF = h->nF, n3 = 3 * nF;
-    k4_peer_indices<<<(unsigned)((n3 + 255) / 256), 256, 0, h->s_compute>>>(
-        pb, h->world, h->rank, half_off, flags_off, epoch, nF, (double)n_total, d_red, d_out5, d_out5 + n3,
-        d_out5 + 2 * n3, d_out5 + 3 * n3, d_out5 + 4 * n3);
-    VH_CUDA(cudaGetLastError());
+    // one launch: block 0 signals this rank's arrival, every block waits for all ranks, then reduces its entries
+    VH_CUDA(vh_launch_pdl(k4_peer_indices, dim3((unsigned)((n3 + 255) / 256)), dim3(256), 0, h->s_compute,
+                          (h->pdl & 8) != 0 && !h->profile, pb, h->world, h->rank, half_off, flags_off, epoch, nF,
+                          (double)n_total, d_red, d_out5, d_out5 + n3, d_out5 + 2 * n3, d_out5 + 3 * n3, d_out5 + 4 * n3,
+                          h->d_sums + VH_NSUM * h->nF, (double)h->count));
     h->launches += 1;
     return VH_OK;
 }
