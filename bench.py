@@ -214,11 +214,17 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     n_total = n_snap * world
     step_no = [0]
 
+    # --wss steps|matrix: K2 also writes tau of every snapshot (72 B per facet and snapshot), as one dolfin vector
+    # per snapshot (WSS.h5) or as rows of the time-major matrix of the spectral tools
+    d_wss = eng.device_alloc(72 * nF * n_snap) if args.wss != "none" else 0
+
     def step_resident():
         d_u = d_copies[step_no[0] % n_copies]
         step_no[0] += 1
         eng.begin(MU, wl["dt"])
-        eng.push_device(d_u, n_snap + halo, stride, flags)
+        if args.wss == "matrix":
+            eng.set_wss_layout(n_snap, 0)
+        eng.push_device(d_u, n_snap + halo, stride, flags, d_wss)
         if comm:
             comm.reduce_finalize(n_total, host=False)  # fused peer reduction + K4 (or ncclAllReduce + K4)
         else:
@@ -294,12 +300,12 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     osi = out["OSI"]
     sane = bool(np.isfinite(out["TAWSS"]).all() and np.nanmin(osi) >= -1e-12 and np.nanmax(osi) <= 0.5 + 1e-12)
 
-    for d in d_copies:
+    for d in d_copies + ([d_wss] if d_wss else []):
         eng.device_free(d)
     if rank != 0:
         return
     peak, peak_src = measured_peak_gbs()
-    b_alg = algorithmic_bytes_per_unit(order)
+    b_alg = algorithmic_bytes_per_unit(order, args.wss != "none")
     units_per_launch = nF * n_snap
     k2_avg_ms = k2_ms / max(k2_n, 1)
     k1_avg_ms = k1_ms / max(k2_n, 1)
@@ -330,7 +336,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {wl['desc']}", "facets": nF, "snapshots_per_gpu": n_snap,
-                   "order": order, "velocity_nodes": int(len(wl["points"])), "wall_layer_nodes": eng.n_wall_nodes,
+                   "order": order, "wss_output": args.wss, "velocity_nodes": int(len(wl["points"])), "wall_layer_nodes": eng.n_wall_nodes,
                    "tets": int(len(wl["tets"])),
                    "parallelism": f"time-shard x{world}",
                    "reduction": ("none" if not comm else "fused peer-memory reduce+finalize (NVLink, CUDA IPC)"
@@ -397,6 +403,8 @@ def main() -> None:
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="stenosis_p1")
     ap.add_argument("--snapshots", type=int, default=None, help="snapshots per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--wss", choices=["none", "steps", "matrix"], default="none",
+                    help="device-resident pass also writes the per-snapshot WSS (default: the metric's indices only)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rules: at least three warm-up steps

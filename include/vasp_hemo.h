@@ -92,11 +92,22 @@ int vh_begin(vh_handle* h, double mu, double dt);
  * K2 grid (0 = auto so that the grid fills 148 SMs). */
 int vh_set_tuning(vh_handle* h, int64_t batch_snapshots, int64_t chunk_snapshots);
 
+/* Layout of the per-snapshot WSS output of the push calls below.
+ *   ld = 0 (default): one dolfin vector per snapshot, [snapshot][facet][boundary dof j][component c] -- what
+ *            WSS.h5 stores (write_checkpoint, compute_hemodynamics.py:285-286).
+ *   ld > 0: the (dof x time) matrix that VaSP's spectral tools build from WSS.h5 by re-reading every step
+ *            (create_transformed_matrix, postprocessing_h5py_common.py:226-246,337-343: row = position in the
+ *            WSS vector, column = snapshot): tau of the k-th non-halo snapshot pushed since this call goes to
+ *            wss_out[(9 f + 3 j + c) * ld + col0 + k]; pass the SAME base pointer to every push.  K2's lanes run
+ *            along time, so these rows are written as full 256-byte lines. */
+int vh_set_wss_layout(vh_handle* h, int64_t ld, int64_t col0);
+
 /* ---- snapshot loop (K2/K3) -------------------------------------------------------------------------------
  * Replaces one or more iterations of the loop at :272-318: P1->P2 transfer, Stress.__call__ (assemble + LU solve
  * + InterpolateDG), |tau| / sum(tau) / TWSSG accumulation.  u: n_snap vectors, consecutive ones stride_bytes
  * apart (pinned memory makes the copies asynchronous; see vh_alloc_pinned).  If wss_out != NULL it receives
- * tau of every non-halo snapshot as [snapshot][facet][boundary dof j][component c] doubles. */
+ * tau of every non-halo snapshot as [snapshot][facet][boundary dof j][component c] doubles (or as columns of the
+ * time-major matrix selected with vh_set_wss_layout). */
 int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t stride_bytes, int flags,
                       double* wss_out);
 /* Same, for vectors already resident in device memory (wss_out is a device pointer or NULL). */

@@ -36,6 +36,7 @@ _SIGNATURES = {
     "vh_get_geometry": [_P, _P, _P, _P],
     "vh_begin": [_P, _DBL, _DBL],
     "vh_set_tuning": [_P, _I64, _I64],
+    "vh_set_wss_layout": [_P, _I64, _I64],
     "vh_push_snapshots": [_P, _P, _I64, _I64, C.c_int, _P],
     "vh_push_snapshots_device": [_P, _P, _I64, _I64, C.c_int, _P],
     "vh_get_sums": [_P, _P, C.POINTER(_I64)],

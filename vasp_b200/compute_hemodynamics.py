@@ -124,7 +124,7 @@ class _BlockReader:
 def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path: Path,
                           mu_f: float, stride: int = 1, velocity_degree: int = 2,
                           device: Optional[int] = None, block_snapshots: Optional[int] = None,
-                          series=None) -> None:
+                          series=None, wss_matrix_folder: Optional[Path] = None) -> None:
     """
     Compute hemodynamic indices from velocity field (reference ``compute_hemodynamics.py:160-372``).
 
@@ -135,6 +135,9 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
         stride (int): Save frequency of output data
         series: (extension) an already opened velocity series, e.g. :class:`io_turtle.TurtleVelocitySeries` over the
             raw turtleFSI output; ``u.h5`` is not needed then and ``stride`` has been applied by whoever opened it
+        wss_matrix_folder: (extension) also write ``wss_mag.npz`` there: the (dof x time) matrix the
+            spectral tools otherwise rebuild from ``WSS.h5`` (``create_transformed_matrix``, quantity ``"wss"``, whole
+            series, stride 1).  K2 then writes tau time-major and the per-step vectors of ``WSS.h5`` are its columns
     """
     rank, local_rank, world = env_rank_world()
     visualization_separate_domain_folder = Path(visualization_separate_domain_folder)
@@ -198,14 +201,27 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
     elif shard.count:
         shard_file = np.lib.format.open_memmap(hemodynamic_indices_path / f".WSS_shard{rank}.npy", mode="w+",
                                                dtype=np.float64, shape=(shard.count, nF, 3, 3))
-    wss_buf = pinned_empty((block_snapshots + 1, nF, 3, 3))
+    direct = None
+    if wss_matrix_folder is not None:
+        assert world == 1, "wss_matrix_folder: the direct WSS matrix is assembled by a single rank"
+        from .wss_matrix import DirectWssMatrix, write_npz
+        ts = [float(t) for t in series.timestamps]
+        direct = DirectWssMatrix(eng, ts, ts[0], ts[-1], 1)
+        direct.attach()
+        wss_buf = None
+    else:
+        wss_buf = pinned_empty((block_snapshots + 1, nF, 3, 3))
 
     reader = _BlockReader(series, shard.read_start, shard.stop, block_snapshots)
     first, done = True, 0
     for a, b, u in reader:
         flags = shard.first_push_flags() if first else 0
         n_real = (b - a) - (1 if (first and shard.has_halo) else 0)
-        eng.push(u, flags=flags, wss_out=wss_buf)
+        if direct is not None:
+            m = eng.push(u, flags=flags)  # columns [done, done + n_real) of the time-major matrix
+            wss_buf = np.ascontiguousarray(m[:, done:done + n_real].T).reshape(n_real, nF, 3, 3)
+        else:
+            eng.push(u, flags=flags, wss_out=wss_buf)
         for r in range(n_real):
             k = shard.start + done + r
             t = float(series.timestamps[k])
@@ -218,6 +234,11 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
         done += n_real
         first = False
     series_io = reader.io_seconds
+    if direct is not None:
+        direct.detach()
+        write_npz(wss_matrix_folder, direct.matrix())
+        if rank == 0:
+            print(f"--- wss_mag.npz is saved in {wss_matrix_folder}")
     if shard_file is not None:
         shard_file.flush()
         del shard_file

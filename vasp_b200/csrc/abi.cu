@@ -313,6 +313,15 @@ int vh_set_tuning(vh_handle* h, int64_t batch_snapshots, int64_t chunk_snapshots
     return VH_OK;
 }
 
+int vh_set_wss_layout(vh_handle* h, int64_t ld, int64_t col0) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_set_wss_layout: null handle");
+    VH_CHECK(ld >= 0 && col0 >= 0 && (ld == 0 ? col0 == 0 : col0 <= ld), VH_ERR_ARG,
+             "vh_set_wss_layout: ld %lld, first column %lld", (long long)ld, (long long)col0);
+    h->wss_ld = ld;
+    h->wss_col = col0;
+    return VH_OK;
+}
+
 // D2H of the five result fields: one copy into a pinned staging buffer (user arrays are usually pageable numpy
 // memory, where every cudaMemcpyAsync degenerates into a staged synchronous copy), then host memcpy
 static int export_out5(vh_handle* h, double* const outs[5]) {
@@ -351,11 +360,16 @@ int vh_push_snapshots_device(vh_handle* h, const double* d_u, int64_t n_snap, in
     int mode = 0;
     VH_TRY(prev_mode_for(h, flags, "vh_push_snapshots_device", &mode));
     const int64_t stride = stride_bytes / 8;
-    if (mode == 2) {
-        VH_CHECK(n_snap >= 2, VH_ERR_ARG, "halo push needs at least one real snapshot after the halo");
-        return k2_launch(h, d_u + stride, n_snap - 1, stride, 2, d_wss_out);
+    VH_CHECK(mode != 2 || n_snap >= 2, VH_ERR_ARG, "halo push needs at least one real snapshot after the halo");
+    const int64_t n_real = n_snap - (mode == 2 ? 1 : 0);
+    if (d_wss_out && h->wss_ld > 0) {
+        VH_CHECK(h->wss_col + n_real <= h->wss_ld, VH_ERR_ARG,
+                 "vh_push_snapshots_device: WSS matrix has %lld columns, %lld already written, %lld more pushed",
+                 (long long)h->wss_ld, (long long)h->wss_col, (long long)n_real);
+        d_wss_out += h->wss_col;
+        h->wss_col += n_real;
     }
-    return k2_launch(h, d_u, n_snap, stride, mode, d_wss_out);
+    return k2_launch(h, mode == 2 ? d_u + stride : d_u, n_real, stride, mode, d_wss_out, h->wss_ld);
 }
 
 int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t stride_bytes, int flags, double* wss_out) {
@@ -370,6 +384,10 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
     const bool halo = mode == 2;
     VH_CHECK(!halo || n_snap >= 2, VH_ERR_ARG, "halo push needs at least one real snapshot after the halo");
     const int64_t nF = h->nF;
+    const bool wss_matrix = wss_out && h->wss_ld > 0;
+    VH_CHECK(!wss_matrix || h->wss_col + n_snap - (halo ? 1 : 0) <= h->wss_ld, VH_ERR_ARG,
+             "vh_push_snapshots: WSS matrix has %lld columns, %lld already written, %lld more pushed",
+             (long long)h->wss_ld, (long long)h->wss_col, (long long)(n_snap - (halo ? 1 : 0)));
 
     // stage capacity: user value, else an eighth of the push (so that the copy of batch i+1 hides behind the kernels
     // of batch i and only the last batch's kernels are exposed), at least 32 snapshots, at most what fits in ~30 %
@@ -450,13 +468,19 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
             n_real = nb - 1;
         }
         cudaEventRecord(k0, h->s_compute);
-        rc = k2_launch(h, d_u, n_real, h->vec_len, pm, wss_out ? h->d_wss_stage[buf] : nullptr);
+        // per-snapshot vectors, or a (9 nF) x stage_cap time-major block whose first n_real columns are copied out
+        rc = k2_launch(h, d_u, n_real, h->vec_len, pm, wss_out ? h->d_wss_stage[buf] : nullptr,
+                       wss_matrix ? h->stage_cap : 0);
         cudaEventRecord(k1, h->s_compute);
         cudaEventRecord(h->ev_consumed[buf], h->s_compute);
         if (rc == VH_OK && wss_out && n_real > 0) {
             cudaStreamWaitEvent(h->s_copy, h->ev_consumed[buf], 0);
-            ce = cudaMemcpyAsync(wss_out + real_done * 9 * nF, h->d_wss_stage[buf], (size_t)(n_real * 72 * nF),
-                                 cudaMemcpyDeviceToHost, h->s_copy);
+            ce = wss_matrix
+                     ? cudaMemcpy2DAsync(wss_out + h->wss_col + real_done, (size_t)(8 * h->wss_ld), h->d_wss_stage[buf],
+                                         (size_t)(8 * h->stage_cap), (size_t)(8 * n_real), (size_t)(9 * nF),
+                                         cudaMemcpyDeviceToHost, h->s_copy)
+                     : cudaMemcpyAsync(wss_out + real_done * 9 * nF, h->d_wss_stage[buf], (size_t)(n_real * 72 * nF),
+                                       cudaMemcpyDeviceToHost, h->s_copy);
             if (ce != cudaSuccess) {
                 vh_set_error("vh_push_snapshots: D2H copy failed: %s", cudaGetErrorString(ce));
                 rc = VH_ERR_CUDA;
@@ -468,6 +492,7 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
         first = false;
         ++b;
     }
+    if (wss_matrix) h->wss_col += real_done;
     cudaError_t e1 = cudaStreamSynchronize(h->s_copy), e2 = cudaStreamSynchronize(h->s_compute);
     if (rc == VH_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
         vh_set_error("vh_push_snapshots: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));

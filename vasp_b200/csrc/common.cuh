@@ -149,6 +149,7 @@ struct vh_handle {
     double* d_part = nullptr;      // [groups][15][nF] partial sums of one launch
     int64_t part_cap = 0;          // capacity in groups
     int64_t batch_snapshots = 0, chunk_snapshots = 0;
+    int64_t wss_ld = 0, wss_col = 0;  // vh_set_wss_layout: leading dimension (0: one vector per snapshot), next column
 
     // staging (double buffered)
     double* d_stage[2] = {nullptr, nullptr};
@@ -188,8 +189,9 @@ int k1_launch(vh_handle* h, const double* d_u, int64_t ncol, int64_t stride_elem
 // ---- K2/K3/K4 (k2_wall.cu) ---------------------------------------------------------------------------------------
 // `n_snap` resident snapshots (d_u + s * stride_elems), staged (K1) and reduced (K2, K3) in column blocks.
 // prev_mode: 0 tau_prev=0, 1 tau_prev from h->d_tau_last, 2 recompute from the snapshot just before d_u (halo).
-// d_wss (may be null): [n_snap][nF][9].
-int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_elems, int prev_mode, double* d_wss);
+// d_wss (may be null): [n_snap][nF][9] if wss_ld == 0, else the (9 nF) x wss_ld time-major matrix (columns 0..n_snap).
+int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_elems, int prev_mode, double* d_wss,
+              int64_t wss_ld);
 int k4_finalize(vh_handle* h, int64_t n_total, double* d_out5);  // d_out5: 5 arrays [nF*3] TAWSS,OSI,RRT,ECAP,TWSSG
 // Fused cross-GPU reduction + final formulas: waits until every rank has signalled `epoch`, adds the partial sums of
 // all ranks in rank order straight from their memory (NVLink peer loads), writes the reduced sums and the indices.

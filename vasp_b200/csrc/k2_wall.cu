@@ -192,7 +192,9 @@ struct K2Args {
     K2Seg multi, single;
     const double* tau_last_in;
     double* tau_last_out;   // [9][nF]
-    double* wss_out;        // [ncol - r0][nF][9] or null
+    double* wss_out;        // tau of every real column, or null: entry (column s, facet f, dof-component i) at
+    int64_t ws_col, ws_f, ws_i;  // wss_out[s * ws_col + f * ws_f + i * ws_i]: {9 nF, 9, 1} = one dolfin vector per
+                                 // snapshot (WSS.h5), {1, 9 ld, ld} = (dof x time) matrix with lanes along a row
     double mu, inv_dt;
 };
 
@@ -328,9 +330,9 @@ __device__ __forceinline__ void k2_body_p2(const K2Args& a, const K2Seg& sg, int
         }
         reduce9(tau, dw, live, live && !(j == 0 && lane == 0 && y > 0), acc);
         if (live && a.wss_out) {
-            double* o = a.wss_out + ((int64_t)(col - a.r0) * nF + f) * 9;
+            double* o = a.wss_out + (int64_t)(col - a.r0) * a.ws_col + f * a.ws_f;
 #pragma unroll
-            for (int i = 0; i < 9; ++i) o[i] = tau[i];
+            for (int i = 0; i < 9; ++i) o[i * a.ws_i] = tau[i];
         }
         if (col == a.ncol - 1) {
 #pragma unroll
@@ -428,14 +430,14 @@ __device__ __forceinline__ void k2_body_multi2(const K2Args& a, const K2Seg& sg,
         reduce9(t1, d1, live1, live1, acc);
         if (a.wss_out) {
             if (live0) {
-                double* o = a.wss_out + ((int64_t)(col - a.r0) * nF + f) * 9;
+                double* o = a.wss_out + (int64_t)(col - a.r0) * a.ws_col + f * a.ws_f;
 #pragma unroll
-                for (int i = 0; i < 9; ++i) o[i] = t0[i];
+                for (int i = 0; i < 9; ++i) o[i * a.ws_i] = t0[i];
             }
             if (live1) {
-                double* o = a.wss_out + ((int64_t)(col + 1 - a.r0) * nF + f) * 9;
+                double* o = a.wss_out + (int64_t)(col + 1 - a.r0) * a.ws_col + f * a.ws_f;
 #pragma unroll
-                for (int i = 0; i < 9; ++i) o[i] = t1[i];
+                for (int i = 0; i < 9; ++i) o[i * a.ws_i] = t1[i];
             }
         }
         if (col == a.ncol - 1 || col + 1 == a.ncol - 1) {
@@ -539,14 +541,14 @@ __device__ __forceinline__ void k2_body_flat2(const K2Args& a, const K2Seg& sg, 
         }
         if (a.wss_out) {
             if (live0) {
-                double* o = a.wss_out + ((int64_t)(col - a.r0) * nF + f) * 9;
+                double* o = a.wss_out + (int64_t)(col - a.r0) * a.ws_col + f * a.ws_f;
 #pragma unroll
-                for (int i = 0; i < 9; ++i) o[i] = t0[i % 3];
+                for (int i = 0; i < 9; ++i) o[i * a.ws_i] = t0[i % 3];
             }
             if (live1) {
-                double* o = a.wss_out + ((int64_t)(col + 1 - a.r0) * nF + f) * 9;
+                double* o = a.wss_out + (int64_t)(col + 1 - a.r0) * a.ws_col + f * a.ws_f;
 #pragma unroll
-                for (int i = 0; i < 9; ++i) o[i] = t1[i % 3];
+                for (int i = 0; i < 9; ++i) o[i * a.ws_i] = t1[i % 3];
             }
         }
         if (col == a.ncol - 1 || col + 1 == a.ncol - 1) {
@@ -881,7 +883,8 @@ int64_t env_int(const char* name, int64_t dflt) {
 
 }  // namespace
 
-int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_elems, int prev_mode, double* d_wss) {
+int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_elems, int prev_mode, double* d_wss,
+              int64_t wss_ld) {
     if (n_snap <= 0) return VH_OK;
     const int64_t nF = h->nF;
     VH_TRY(ensure_stage_block(h, n_snap + 1));
@@ -933,7 +936,10 @@ int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_el
         a.tau_last_in = h->d_tau_last[h->tau_cur];
         a.tau_last_out = h->d_tau_last[h->tau_cur ^ 1];
         h->tau_cur ^= 1;
-        a.wss_out = d_wss ? d_wss + pos * nF * 9 : nullptr;
+        a.ws_col = wss_ld > 0 ? 1 : 9 * nF;
+        a.ws_f = wss_ld > 0 ? 9 * wss_ld : 9;
+        a.ws_i = wss_ld > 0 ? wss_ld : 1;
+        a.wss_out = d_wss ? d_wss + pos * a.ws_col : nullptr;
         a.mu = h->mu;
         a.inv_dt = 1.0 / h->dt;
         if (h->order == 2)

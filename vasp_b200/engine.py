@@ -141,11 +141,42 @@ class HemoEngine:
     def set_tuning(self, batch_snapshots: int = 0, chunk_snapshots: int = 0) -> None:
         check(self._lib.vh_set_tuning(self._h, int(batch_snapshots), int(chunk_snapshots)))
 
+    def set_wss_matrix(self, matrix: Optional[np.ndarray], first_column: int = 0) -> None:
+        """Select the layout of the WSS output of :meth:`push`.
+
+        ``matrix`` = C-contiguous float64 (9 nF, n_cols) array (ideally pinned): tau of the k-th non-halo snapshot
+        pushed from now on becomes column ``first_column + k``, row ``9 f + 3 j + c`` -- the (dof x time) matrix
+        VaSP's spectral tools build from WSS.h5 (``create_transformed_matrix``,
+        postprocessing_h5py_common.py:226-246,337-343).  ``None`` restores one vector per snapshot."""
+        if matrix is None:
+            self._wss_matrix = None
+            check(self._lib.vh_set_wss_layout(self._h, 0, 0))
+            return
+        if (matrix.dtype != np.float64 or matrix.ndim != 2 or not matrix.flags.c_contiguous
+                or matrix.shape[0] != 9 * self.nF):
+            raise ValueError("WSS matrix must be C-contiguous float64 with 9*nF rows")
+        check(self._lib.vh_set_wss_layout(self._h, int(matrix.shape[1]), int(first_column)))
+        self._wss_matrix = matrix
+
+    def set_wss_layout(self, ld: int, first_column: int = 0) -> None:
+        """Raw form of :meth:`set_wss_matrix` for device-resident output (:meth:`push_device`)."""
+        check(self._lib.vh_set_wss_layout(self._h, int(ld), int(first_column)))
+
     def push(self, u: np.ndarray, flags: int = 0, keep_wss: bool = False,
              wss_out: Optional[np.ndarray] = None) -> Optional[np.ndarray]:
         """Process ``u`` = (n_snap, >= vec_len) float64 rows (ideally a :func:`pinned_empty` buffer).
 
-        Returns tau of every non-halo snapshot as (n, nF, 3 dofs, 3 comps) when ``keep_wss``."""
+        Returns tau of every non-halo snapshot as (n, nF, 3 dofs, 3 comps) when ``keep_wss``; after
+        :meth:`set_wss_matrix` the snapshots become columns of that matrix instead (and it is returned)."""
+        if getattr(self, "_wss_matrix", None) is not None:
+            if wss_out is not None or keep_wss:
+                raise ValueError("set_wss_matrix() is active: the WSS output goes to that matrix")
+            if u.dtype != np.float64 or u.ndim != 2 or u.strides[1] != 8 or u.shape[1] < self.vec_len:
+                raise ValueError("u must be a 2-D float64 array with contiguous rows of at least vec_len entries")
+            stride = u.strides[0] if u.shape[0] > 1 else u.shape[1] * 8
+            check(self._lib.vh_push_snapshots(self._h, _ptr(u), u.shape[0], stride, int(flags),
+                                              _ptr(self._wss_matrix)))
+            return self._wss_matrix
         if u.dtype != np.float64 or u.ndim != 2 or u.strides[1] != 8:
             raise ValueError("u must be a 2-D float64 array with contiguous rows")
         if u.shape[1] < self.vec_len:
