@@ -365,7 +365,106 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                                                        if k1_avg_ms > 0 else None)}},
         "cpu_baseline": cpu,
     }
+    if world == 1 and not args.no_io_leg:
+        eng.close()
+        try:
+            line["io"] = io_leg(wl, n_snap, u_host, local_rank)
+        except Exception as e:  # the headline line must not depend on the scratch file system
+            line["io"] = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps(line), flush=True)
+
+
+def io_leg(wl, n_snap: int, u_host: np.ndarray, device: int):
+    """HDF5 -> device, timed apart from the device-resident compute (north_star; SURVEY.md §8d "Timers").
+
+    A `u.h5` in the layout create_hdf5.py:158-174 writes is produced from the same synthetic series (bounded to
+    ~1 GiB), then read back through the path the drop-in CLI uses: raw `pread` into two pinned buffers one block
+    ahead of the consumer, H2D on the copy stream, kernels on the compute stream.  Reported: open -> last result for a
+    cold page cache (pages dropped with posix_fadvise) and a warm one, and -- third -- the whole entry point
+    `compute_hemodyanamics()` including the six XDMF/HDF5 outputs (per-step WSS.h5 included)."""
+    import os
+    import shutil
+    import tempfile
+    from vasp_b200 import io_dolfin
+    from vasp_b200.compute_hemodynamics import _BlockReader, compute_hemodyanamics, default_block_snapshots
+    from vasp_b200.engine import HemoEngine
+    from vasp_b200.h5lite import H5Writer
+    import contextlib
+    import io as _io
+
+    order, vec_len = wl["order"], u_host.shape[1]
+    n_io = int(max(3, min(n_snap, (1 << 30) // (vec_len * 8))))
+    tmp = Path(tempfile.mkdtemp(prefix="vasp_b200_io_"))
+    try:
+        (tmp / "Mesh").mkdir()
+        vsd = tmp / "Visualization_separate_domain"
+        vsd.mkdir()
+        io_dolfin.write_mesh(tmp / "Mesh" / "mesh.h5", wl["xyz"], wl["tets"])
+        io_dolfin.write_mesh(tmp / "Mesh" / "mesh_fluid.h5", wl["xyz"], wl["tets"])
+        if order == 2:  # only the coordinates of the refined mesh are used when u.h5 carries no dof tables
+            io_dolfin.write_mesh(tmp / "Mesh" / "mesh_refined_fluid.h5", wl["points"], wl["tets"][:1])
+        rows = u_host[wl["halo"]:wl["halo"] + n_io]
+        with H5Writer(vsd / "u.h5") as w:
+            for k in range(n_io):
+                w.create_dataset(f"/velocity/vector_{k}", rows[k],
+                                 attrs={"timestamp": float((k + 1) * wl["dt"]), "partition": np.array([0], dtype=np.uint64)})
+        path = vsd / "u.h5"
+        nbytes = n_io * vec_len * 8
+
+        def drop_cache():
+            fd = os.open(path, os.O_RDONLY)
+            try:
+                os.fsync(fd)
+                os.posix_fadvise(fd, 0, 0, os.POSIX_FADV_DONTNEED)
+            finally:
+                os.close(fd)
+
+        eng = HemoEngine(device)
+        eng.set_mesh(wl["xyz"], wl["tets"])
+        eng.set_velocity_layout(order, refined_xyz=wl["points"] if order == 2 else None)
+        block = default_block_snapshots(vec_len)
+        eng.set_tuning(batch_snapshots=block, chunk_snapshots=0)
+
+        def run_once():
+            t0 = time.perf_counter()
+            series = io_dolfin.VelocitySeries(path, "velocity", 1)
+            eng.begin(MU, float(series.timestamps[1] - series.timestamps[0]))
+            reader = _BlockReader(series, 0, len(series), block)
+            first = True
+            for a, b, u in reader:
+                eng.push(u, flags=1 if first else 0)
+                first = False
+            out = eng.finalize(len(series))
+            dt_s = time.perf_counter() - t0
+            tm = eng.timers()
+            series.close()
+            return dt_s, reader.io_seconds, tm, out
+
+        res = {}
+        for label in ("cold", "warm", "warm"):
+            if label == "cold":
+                drop_cache()
+            dt_s, io_s, tm, out = run_once()
+            res[label] = {"open_to_result_s": dt_s, "file_read_s": io_s, "h2d_s": tm["h2d_ms"] * 1e-3,
+                          "kernels_s": tm["kernel_ms"] * 1e-3, "gbs": nbytes / dt_s / 1e9,
+                          "value": eng.nF * n_io / dt_s}
+        nF = eng.nF
+        eng.close()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(_io.StringIO()):
+            compute_hemodyanamics(vsd, tmp / "Mesh" / "mesh.h5", MU, 1, velocity_degree=order, device=device)
+        cli_s = time.perf_counter() - t0
+        out_bytes = sum(f.stat().st_size for f in (tmp / "Hemodynamic_indices").iterdir())
+        return {"file": "u.h5 (create_hdf5 layout), synthetic", "snapshots": n_io, "bytes": nbytes,
+                "block_snapshots": block, "unit": UNIT, "hdf5_to_device": res,
+                "page_cache": "cold = pages dropped with posix_fadvise(DONTNEED) before the run; warm = second of two "
+                              "runs over the file just read",
+                "entry_point": {"total_s": cli_s, "value": nF * n_io / cli_s, "output_bytes": out_bytes,
+                                "what": "compute_hemodyanamics(): mesh + u.h5 in, K0, time loop, WSS.h5 per step and "
+                                        "the five index files out"},
+                "scratch": str(tmp.parent)}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def cpu_baseline(wl, n_snap: int):
@@ -403,6 +502,7 @@ def main() -> None:
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="stenosis_p1")
     ap.add_argument("--snapshots", type=int, default=None, help="snapshots per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-io-leg", action="store_true", help="skip the HDF5 -> device and entry-point timings")
     ap.add_argument("--wss", choices=["none", "steps", "matrix"], default="none",
                     help="device-resident pass also writes the per-snapshot WSS (default: the metric's indices only)")
     args = ap.parse_args()

@@ -96,6 +96,38 @@ def test_velocity_layout_detection(tmp_path, kind):
     s.close()
 
 
+def test_series_reads_in_pieces_over_a_thread_pool(tmp_path, monkeypatch):
+    """The CLI's block reader cuts long vectors and groups short ones into ~4 MiB jobs for several pread threads
+    (vasp_b200/io_dolfin.py read_chunks); whatever the cut, the rows must come back byte for byte."""
+    from concurrent.futures import ThreadPoolExecutor
+    from vasp_b200 import compute_hemodynamics as ch
+    from vasp_b200.compute_hemodynamics import _BlockReader, default_block_snapshots
+    monkeypatch.setattr(ch, "pinned_empty", lambda shape: np.zeros(shape))   # no CUDA driver in the CPU suite
+    rng = np.random.default_rng(8)
+    n, n_snap = 211, 23
+    vecs = rng.normal(size=(n_snap, 3 * n))
+    p = tmp_path / "u.h5"
+    with H5Writer(p) as w:
+        for k in range(n_snap):
+            w.create_dataset(f"/velocity/vector_{k}", vecs[k], attrs={"timestamp": 0.1 * k})
+    s = io_dolfin.VelocitySeries(p)
+    for chunk in (64, 1000, 3 * n * 8, 10 ** 6):
+        jobs = s.read_chunks(np.zeros((5, 3 * n)), 3, 8, chunk_bytes=chunk)
+        assert sum(len(mv) for job in jobs for mv, _ in job) == 5 * 3 * n * 8
+        assert all(sum(len(mv) for mv, _ in job) >= min(chunk, 8) for job in jobs[:-1])
+    buf = np.zeros((n_snap, 3 * n + 3))
+    with ThreadPoolExecutor(3) as pool:
+        s.read_into(buf, 0, n_snap, pool)
+    assert np.array_equal(buf[:, :3 * n], vecs) and (buf[:, 3 * n:] == 0).all()
+    got = []
+    for a, b, u in _BlockReader(s, 2, n_snap, 4):   # two buffers, one block ahead; no single trailing snapshot
+        assert b - a >= 2
+        got.append(np.array(u[:, :3 * n]))
+    assert np.array_equal(np.concatenate(got), vecs[2:])
+    assert default_block_snapshots(3 * 2997) == 233 and default_block_snapshots(3 * 13_400_000) == 2
+    s.close()
+
+
 def test_checkpoint_writer_layout(tmp_path):
     """Member names and shapes the reference's own consumer dereferences
     (postprocessing_h5py_common.py:234-242,271,337-343) and regexes it parses XDMF with

@@ -22,8 +22,10 @@ from __future__ import annotations
 import argparse
 import json
 import logging
+import os
 import threading
 import time
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 from typing import Dict, Optional, Union
 
@@ -71,6 +73,13 @@ def read_parameters_from_file(folder: Union[str, Path]) -> Optional[Dict]:
         return None
 
 
+def default_block_snapshots(vec_len: int) -> int:
+    """Snapshots per pinned read buffer: ~16 MiB, at least 2 and at most 512.  Small blocks matter twice: nothing
+    overlaps the first block's read, and pinning memory costs about as much per byte as reading it (measured:
+    2 x 260 MB buffers cost more than reading the 1 GB file from the page cache, profiles/r1io_*)."""
+    return int(min(512, max(2, (16 << 20) // (vec_len * 8))))
+
+
 class _BlockReader:
     """Reads snapshot blocks of ``u.h5`` into two pinned buffers, one block ahead of the consumer."""
 
@@ -87,6 +96,9 @@ class _BlockReader:
         rows = max((b - a for a, b in self.ranges), default=1)
         self.bufs = [pinned_empty((rows, series.vec_len)) for _ in range(2)]
         self.io_seconds = 0.0
+        # page cache -> pinned memory is a memcpy per pread: one thread moves ~7 GB/s, the PCIe link takes 52
+        n_threads = int(os.environ.get("VASP_B200_READ_THREADS", min(4, os.cpu_count() or 1)))
+        self._pool = ThreadPoolExecutor(n_threads) if n_threads > 1 else None
         self._ready = [threading.Event(), threading.Event()]
         self._free = [threading.Event(), threading.Event()]
         for e in self._free:
@@ -102,13 +114,16 @@ class _BlockReader:
                 self._free[slot].wait()
                 self._free[slot].clear()
                 t0 = time.perf_counter()
-                self.series.read_into(self.bufs[slot], a, b)
+                self.series.read_into(self.bufs[slot], a, b, self._pool)
                 self.io_seconds += time.perf_counter() - t0
                 self._ready[slot].set()
         except BaseException as e:  # surfaced in the consumer
             self._error = e
             for e2 in self._ready:
                 e2.set()
+        finally:
+            if self._pool is not None:
+                self._pool.shutdown(wait=False)
 
     def __iter__(self):
         for i, (a, b) in enumerate(self.ranges):
@@ -190,8 +205,7 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
     shard = plan_shard(n_snap, rank, world)
     nF = eng.nF
     if block_snapshots is None:
-        # ~256 MiB of pinned memory per buffer, at least 2 and at most 512 snapshots
-        block_snapshots = int(min(512, max(2, (256 << 20) // (series.vec_len * 8))))
+        block_snapshots = default_block_snapshots(series.vec_len)
     eng.set_tuning(batch_snapshots=block_snapshots, chunk_snapshots=0)
 
     wss_writer = None

@@ -128,19 +128,44 @@ class VelocitySeries:
             return (0, n_nodes, 2 * n_nodes), 1, q
         raise ValueError(f"{self.path}: unsupported dof numbering in cell_dofs")
 
-    def read_into(self, out: np.ndarray, first: int, last: int) -> np.ndarray:
-        """Raw ``pread`` of snapshots ``[first, last)`` into the rows of ``out`` (no HDF5 library in the loop)."""
-        fd = self._f._fh.fileno()
+    def read_chunks(self, out: np.ndarray, first: int, last: int, chunk_bytes: int = 4 << 20):
+        """Jobs of about ``chunk_bytes`` -- each a list of ``(memoryview, file offset)`` pieces -- that together fill
+        rows ``0 .. last-first`` of ``out`` with snapshots ``[first, last)``; independent of each other, so several
+        threads can ``pread`` them (long vectors are cut, short ones grouped)."""
         nbytes = self.vec_len * 8
+        jobs, cur, cur_bytes = [], [], 0
         for r, k in enumerate(range(first, last)):
-            row = out[r, :self.vec_len]
-            mv = memoryview(row).cast("B")
-            got = 0
-            while got < nbytes:
-                n = os.preadv(fd, [mv[got:]], int(self.offsets[k]) + got)
+            mv = memoryview(out[r, :self.vec_len]).cast("B")
+            for lo in range(0, nbytes, chunk_bytes):
+                hi = min(lo + chunk_bytes, nbytes)
+                cur.append((mv[lo:hi], int(self.offsets[k]) + lo))
+                cur_bytes += hi - lo
+                if cur_bytes >= chunk_bytes:
+                    jobs.append(cur)
+                    cur, cur_bytes = [], 0
+        if cur:
+            jobs.append(cur)
+        return jobs
+
+    def pread_chunk(self, job) -> None:
+        fd = self._f._fh.fileno()
+        for mv, off in job:
+            got, n_all = 0, len(mv)
+            while got < n_all:
+                n = os.preadv(fd, [mv[got:]], off + got)  # releases the GIL
                 if n <= 0:
-                    raise IOError(f"{self.path}: short read in {self.names[k]}")
+                    raise IOError(f"{self.path}: short read at offset {off + got}")
                 got += n
+
+    def read_into(self, out: np.ndarray, first: int, last: int, pool=None) -> np.ndarray:
+        """Raw ``pread`` of snapshots ``[first, last)`` into the rows of ``out`` (no HDF5 library in the loop);
+        ``pool`` (a ``ThreadPoolExecutor``) spreads the pieces over its threads."""
+        jobs = self.read_chunks(out, first, last)
+        if pool is None or len(jobs) < 2:
+            for j in jobs:
+                self.pread_chunk(j)
+        else:
+            list(pool.map(self.pread_chunk, jobs))
         return out
 
     def close(self) -> None:

@@ -138,16 +138,36 @@ class TurtleVelocitySeries:
                              f"{n_nodes} vertices")
         return (0, 1, 2), 3, self.fluid_ids.astype(np.int64)
 
-    def read_into(self, out: np.ndarray, first: int, last: int) -> np.ndarray:
-        nbytes = self.vec_len * 8
+    def read_into(self, out: np.ndarray, first: int, last: int, pool=None) -> np.ndarray:
+        """Same contract as :meth:`io_dolfin.VelocitySeries.read_into`: pieces of ~4 MiB, spread over ``pool``."""
+        nbytes, chunk = self.vec_len * 8, 4 << 20
+        jobs, cur, cur_bytes = [], [], 0
         for r, k in enumerate(range(first, last)):
             mv = memoryview(out[r, :self.vec_len]).cast("B")
-            got = 0
-            while got < nbytes:
-                n = os.preadv(self._fd[k], [mv[got:]], int(self.offsets[k]) + got)
-                if n <= 0:
-                    raise IOError(f"{self.path}: short read in {self.names[k]}")
-                got += n
+            for lo in range(0, nbytes, chunk):
+                hi = min(lo + chunk, nbytes)
+                cur.append((mv[lo:hi], self._fd[k], int(self.offsets[k]) + lo))
+                cur_bytes += hi - lo
+                if cur_bytes >= chunk:
+                    jobs.append(cur)
+                    cur, cur_bytes = [], 0
+        if cur:
+            jobs.append(cur)
+
+        def run(job) -> None:
+            for mv, fd, off in job:
+                got, n_all = 0, len(mv)
+                while got < n_all:
+                    n = os.preadv(fd, [mv[got:]], off + got)
+                    if n <= 0:
+                        raise IOError(f"{self.path}: short read at offset {off + got}")
+                    got += n
+
+        if pool is None or len(jobs) < 2:
+            for j in jobs:
+                run(j)
+        else:
+            list(pool.map(run, jobs))
         return out
 
     def close(self) -> None:
