@@ -450,16 +450,22 @@ def io_leg(wl, n_snap: int, u_host: np.ndarray, device: int):
                           "value": eng.nF * n_io / dt_s}
         nF = eng.nF
         eng.close()
-        t0 = time.perf_counter()
-        with contextlib.redirect_stdout(_io.StringIO()):
-            compute_hemodyanamics(vsd, tmp / "Mesh" / "mesh.h5", MU, 1, velocity_degree=order, device=device)
-        cli_s = time.perf_counter() - t0
+        runs = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            log = _io.StringIO()
+            with contextlib.redirect_stdout(log):
+                compute_hemodyanamics(vsd, tmp / "Mesh" / "mesh.h5", MU, 1, velocity_degree=order, device=device)
+            runs.append((time.perf_counter() - t0,
+                         next((ln for ln in log.getvalue().splitlines() if ln.startswith("--- timing")), "")))
+        cli_s, cli_line = min(runs)
         out_bytes = sum(f.stat().st_size for f in (tmp / "Hemodynamic_indices").iterdir())
         return {"file": "u.h5 (create_hdf5 layout), synthetic", "snapshots": n_io, "bytes": nbytes,
                 "block_snapshots": block, "unit": UNIT, "hdf5_to_device": res,
                 "page_cache": "cold = pages dropped with posix_fadvise(DONTNEED) before the run; warm = second of two "
                               "runs over the file just read",
-                "entry_point": {"total_s": cli_s, "value": nF * n_io / cli_s, "output_bytes": out_bytes,
+                "entry_point": {"total_s": cli_s, "runs_s": [r[0] for r in runs], "breakdown": cli_line,
+                                "value": nF * n_io / cli_s, "output_bytes": out_bytes,
                                 "what": "compute_hemodyanamics(): mesh + u.h5 in, K0, time loop, WSS.h5 per step and "
                                         "the five index files out"},
                 "scratch": str(tmp.parent)}

@@ -111,14 +111,18 @@ def test_multi_facet_cells_solve_the_dense_block_system():
     S = ho.SurfaceStress(xyz, tets, 1.3, 2)
     u = synth.velocity_series(synth.velocity_basis(pts, seed=4), np.array([[1.0, 0.5, -0.3, 0.2]]))[0]
     tau = S(u, (0, n, 2 * n))
-    # degree-4 Strang-Fix rule
+    _dense_block_check(S, u, tau, cn, n, np.nonzero(S.maps.n_ext == 2)[0][:10])
+    assert ho.order_cells(tets).shape == (len(tets), 4)
+
+
+def _dense_block_check(S, u, tau, cn, n, wall_cells):
+    """Re-assemble the SurfaceProjector block A and the right-hand side b of the given wall cells densely with a
+    degree-4 Strang-Fix rule (the oracle uses FFC's 3-point rule) and solve; P2 data."""
     a1, a2 = 0.816847572980459, 0.091576213509771
     b1, b2 = 0.108103018168070, 0.445948490915965
     pts4 = np.array([[a1, a2, a2], [a2, a1, a2], [a2, a2, a1], [b1, b2, b2], [b2, b1, b2], [b2, b2, b1]])
     wts4 = np.array([0.109951743655322] * 3 + [0.223381589678011] * 3)
-    multi_cells = np.nonzero(S.maps.n_ext == 2)[0][:10]
-    t = ho.order_cells(tets)
-    for w in multi_cells:
+    for w in wall_cells:
         fs = np.nonzero(S.facet_wall == w)[0]
         A, b = np.zeros((4, 4)), np.zeros((4, 3))
         cell = S.maps.wall_cells[w]
@@ -136,7 +140,25 @@ def test_multi_facet_cells_solve_the_dense_block_system():
         xsol = np.linalg.solve(A, b)
         for f in fs:
             assert np.allclose(tau[f], xsol[S.maps.bcell_local[f].astype(int)], rtol=1e-11, atol=1e-13)
-        assert t[cell].shape == (4,)
+
+
+@pytest.mark.parametrize("name", ["one_tet", "two_tets", "cube5", "cube6"])
+def test_cells_with_three_and_four_exterior_facets(name):
+    """The reference meshes only have cells with two exterior facets; a lone tetrahedron has four (no identity row is
+    left in its block), the corner cells of a 5-tet cube three.  Same dense check."""
+    from tests.test_gpu_tiny_meshes import MESHES
+    xyz, tets = MESHES[name]
+    tets = tets.astype(np.int64)
+    cn, edges = ho.p2_cell_nodes(tets)
+    pts = ho.p2_node_coordinates(xyz, edges)
+    n = len(pts)
+    rng = np.random.default_rng(2)
+    u = np.concatenate([(pts @ rng.normal(size=3) + np.einsum("nj,jk,nk->n", pts, rng.normal(size=(3, 3)), pts))
+                        for _ in range(3)])
+    S = ho.SurfaceStress(xyz, tets, 0.7, 2)
+    tau = S(u, (0, n, 2 * n))
+    assert S.maps.n_ext.max() == {"one_tet": 4, "two_tets": 3, "cube5": 3, "cube6": 2}[name]
+    _dense_block_check(S, u, tau, cn, n, np.nonzero(S.maps.n_ext >= 2)[0])
 
 
 @pytest.mark.parametrize("order", [2, 1])

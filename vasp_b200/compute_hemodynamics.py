@@ -228,14 +228,19 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
 
     reader = _BlockReader(series, shard.read_start, shard.stop, block_snapshots)
     first, done = True, 0
+    t_setup = time.perf_counter() - t_begin
+    t_push = t_write = 0.0
     for a, b, u in reader:
         flags = shard.first_push_flags() if first else 0
         n_real = (b - a) - (1 if (first and shard.has_halo) else 0)
+        t0 = time.perf_counter()
         if direct is not None:
             m = eng.push(u, flags=flags)  # columns [done, done + n_real) of the time-major matrix
             wss_buf = np.ascontiguousarray(m[:, done:done + n_real].T).reshape(n_real, nF, 3, 3)
         else:
             eng.push(u, flags=flags, wss_out=wss_buf)
+        t1 = time.perf_counter()
+        t_push += t1 - t0
         for r in range(n_real):
             k = shard.start + done + r
             t = float(series.timestamps[k])
@@ -245,6 +250,7 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
                 wss_writer.write(wss_buf[r], t)
             else:
                 shard_file[done + r] = wss_buf[r]
+        t_write += time.perf_counter() - t1
         done += n_real
         first = False
     series_io = reader.io_seconds
@@ -285,8 +291,9 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
             w.close()
             print(f"--- {name} is saved in {hemodynamic_indices_path}")
         total = time.perf_counter() - t_begin
-        print(f"--- timing: total {total:.3f} s | u.h5 -> pinned host {series_io:.3f} s | host -> device "
-              f"{timers['h2d_ms'] * 1e-3:.3f} s | kernels {timers['kernel_ms'] * 1e-3:.3f} s | "
+        print(f"--- timing: total {total:.3f} s | mesh + maps {t_setup:.3f} s | u.h5 -> pinned host {series_io:.3f} s "
+              f"(reader thread) | push calls {t_push:.3f} s (host -> device {timers['h2d_ms'] * 1e-3:.3f} s, kernels "
+              f"{timers['kernel_ms'] * 1e-3:.3f} s) | WSS.h5 steps {t_write:.3f} s | "
               f"{nF} wall facets x {n_snap} snapshots on {world} GPU(s)")
     eng.close()
 
