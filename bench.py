@@ -70,7 +70,7 @@ def measured_peak_gbs():
 class ClockSampler:
     """NVML samples of SM clock and throttle reasons while the timed region runs."""
 
-    def __init__(self, index: int, period_s: float = 0.005):
+    def __init__(self, index: int, period_s: float = 0.002):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._thread = None
