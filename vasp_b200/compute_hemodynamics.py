@@ -206,6 +206,10 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
     nF = eng.nF
     if block_snapshots is None:
         block_snapshots = default_block_snapshots(series.vec_len)
+        if wss_matrix_folder is not None:
+            # the matrix comes back as a pitched copy of 9 nF rows of (block x 8) bytes: keep the rows >= 256 bytes
+            # unless that would pin more than 1 GiB per read buffer
+            block_snapshots = max(block_snapshots, min(32, max(2, (1 << 30) // (series.vec_len * 8))))
     eng.set_tuning(batch_snapshots=block_snapshots, chunk_snapshots=0)
 
     wss_writer = None

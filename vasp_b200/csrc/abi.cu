@@ -141,6 +141,7 @@ int vh_create(int device, vh_handle** out) {
     if (const char* e = getenv("VASP_B200_PDL")) h->pdl = atoi(e);
     VH_CUDA(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
     VH_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    VH_CUDA(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
     VH_CUDA(cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking));
     VH_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     VH_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
@@ -184,6 +185,7 @@ int vh_destroy(vh_handle* h) {
     cudaEventDestroy(h->ev_join);
     cudaStreamDestroy(h->s_compute);
     cudaStreamDestroy(h->s_copy);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     cudaStreamDestroy(h->s_aux);
     delete h;
     return VH_OK;
@@ -474,18 +476,20 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
         cudaEventRecord(k1, h->s_compute);
         cudaEventRecord(h->ev_consumed[buf], h->s_compute);
         if (rc == VH_OK && wss_out && n_real > 0) {
-            cudaStreamWaitEvent(h->s_copy, h->ev_consumed[buf], 0);
+            // on its own stream: on the copy stream the next batch's H2D would queue behind this D2H, which waits for
+            // this batch's kernels, and nothing would overlap (PCIe is full duplex, the GPU has several copy engines)
+            cudaStreamWaitEvent(h->s_d2h, h->ev_consumed[buf], 0);
             ce = wss_matrix
                      ? cudaMemcpy2DAsync(wss_out + h->wss_col + real_done, (size_t)(8 * h->wss_ld), h->d_wss_stage[buf],
                                          (size_t)(8 * h->stage_cap), (size_t)(8 * n_real), (size_t)(9 * nF),
-                                         cudaMemcpyDeviceToHost, h->s_copy)
+                                         cudaMemcpyDeviceToHost, h->s_d2h)
                      : cudaMemcpyAsync(wss_out + real_done * 9 * nF, h->d_wss_stage[buf], (size_t)(n_real * 72 * nF),
-                                       cudaMemcpyDeviceToHost, h->s_copy);
+                                       cudaMemcpyDeviceToHost, h->s_d2h);
             if (ce != cudaSuccess) {
                 vh_set_error("vh_push_snapshots: D2H copy failed: %s", cudaGetErrorString(ce));
                 rc = VH_ERR_CUDA;
             }
-            cudaEventRecord(h->ev_wss[buf], h->s_copy);
+            cudaEventRecord(h->ev_wss[buf], h->s_d2h);
         }
         real_done += n_real;
         pos += nb;
@@ -494,6 +498,8 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
     }
     if (wss_matrix) h->wss_col += real_done;
     cudaError_t e1 = cudaStreamSynchronize(h->s_copy), e2 = cudaStreamSynchronize(h->s_compute);
+    const cudaError_t e3 = cudaStreamSynchronize(h->s_d2h);
+    if (e1 == cudaSuccess) e1 = e3;
     if (rc == VH_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
         vh_set_error("vh_push_snapshots: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
         rc = VH_ERR_CUDA;

@@ -84,6 +84,7 @@ struct vh_handle {
     int device = 0;
     int sm_count = 148;
     cudaStream_t s_compute = nullptr, s_copy = nullptr, s_aux = nullptr;  // s_aux: multi-facet-cell K2 launch
+    cudaStream_t s_d2h = nullptr;  // WSS blocks back to the host: its own stream, so that the next H2D does not queue behind it
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     // mesh
