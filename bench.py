@@ -279,6 +279,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
 
     # end to end through the public API: pinned host snapshots in, five result fields out
     e2e_steps = max(1, min(args.steps, 10))
+    if os.environ.get("VASP_B200_E2E_BATCH"):  # experiments: snapshots per host->device batch (default: auto)
+        eng.set_tuning(batch_snapshots=int(os.environ["VASP_B200_E2E_BATCH"]))
     step_e2e()
     eng.sync()
     if comm:
