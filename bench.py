@@ -302,6 +302,10 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     osi = out["OSI"]
     sane = bool(np.isfinite(out["TAWSS"]).all() and np.nanmin(osi) >= -1e-12 and np.nanmax(osi) <= 0.5 + 1e-12)
 
+    reduction = ("none" if not comm else "fused peer-memory reduce+finalize (NVLink, CUDA IPC)" if comm.fused
+                 else "ncclAllReduce + finalize")
+    if comm:
+        comm.close()  # collective teardown while every rank is alive (rank 0 still has the JSON line to assemble)
     for d in d_copies + ([d_wss] if d_wss else []):
         eng.device_free(d)
     if rank != 0:
@@ -341,8 +345,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                    "order": order, "wss_output": args.wss, "velocity_nodes": int(len(wl["points"])), "wall_layer_nodes": eng.n_wall_nodes,
                    "tets": int(len(wl["tets"])),
                    "parallelism": f"time-shard x{world}",
-                   "reduction": ("none" if not comm else "fused peer-memory reduce+finalize (NVLink, CUDA IPC)"
-                                 if comm.fused else "ncclAllReduce + finalize"), 
+                   "reduction": reduction, 
                    "l2": (f"{n_copies} rotating resident copies of the input ({n_copies * u_host.nbytes / 1e6:.0f} MB > "
                           f"2.5 x 126 MB L2), steps back to back" if n_copies > 1 else
                           f"input {u_host.nbytes / 1e6:.0f} MB per step, larger than 2 x 126 MB L2"),

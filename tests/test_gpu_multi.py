@@ -92,3 +92,49 @@ def test_two_gpu_time_shards_fused_and_nccl(engine_lib, tmp_path, order):
         assert p.returncode == 0, o
     a, b = np.load(str(tmp_path / "res") + ".fused0.npy"), np.load(str(tmp_path / "res") + ".fused1.npy")
     assert np.array_equal(a, b), "fused reduction must be bitwise identical on every rank"
+
+
+def test_entry_point_under_two_ranks_writes_the_same_files(engine_lib, tmp_path):
+    """The drop-in entry point launched the way INTEGRATION.md says (one process per GPU, torchrun-style environment):
+    time shards with a halo snapshot, per-shard WSS blocks merged by rank 0, fused reduction -- the six outputs must
+    equal those of a single-rank run (WSS steps bitwise, indices to summation order)."""
+    if _gpu_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    import shutil
+    import numpy as np
+    from tests.test_gpu_cli import _make_folder
+    from vasp_b200 import io_dolfin, synth
+    cache = {}
+
+    def u_syn(p, t):
+        if "b" not in cache:
+            cache["b"] = synth.velocity_basis(p, seed=9)
+        coef = np.array([[1 + 0.6 * np.sin(2 * np.pi * t), 0.2 * np.sin(4 * np.pi * t + 1), 0.1 * np.cos(6 * np.pi * t),
+                          0.3 * np.sin(2 * np.pi * t + 2)]])
+        return synth.velocity_series(cache["b"], coef)[0]
+
+    one, two = tmp_path / "one", tmp_path / "two"
+    one.mkdir()
+    _make_folder(one, u_syn, 23, 0.04, 3.5e-3)
+    shutil.copytree(one, two)
+    subprocess.check_output([sys.executable, "-m", "vasp_b200.compute_hemodynamics", "--folder", str(one)], cwd=ROOT)
+    port = _free_port()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-m", "vasp_b200.compute_hemodynamics", "--folder", str(two)],
+                                      cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+    assert "Calculating WSS at Timestep" in outs[0] and "Calculating WSS at Timestep" not in outs[1]  # rank-0 prints
+    h1, h2 = one / "Hemodynamic_indices", two / "Hemodynamic_indices"
+    assert sorted(f.name for f in h2.iterdir()) == sorted(f.name for f in h1.iterdir())   # no shard files left behind
+    for k in range(23):
+        a, b = io_dolfin.read_checkpoint(h1, "WSS", k), io_dolfin.read_checkpoint(h2, "WSS", k)
+        assert np.array_equal(a["values"], b["values"]), k
+    assert (h1 / "WSS.xdmf").read_text() == (h2 / "WSS.xdmf").read_text()
+    for name in ("TAWSS", "OSI", "RRT", "ECAP", "TWSSG"):
+        a, b = io_dolfin.read_checkpoint(h1, name, 0)["values"], io_dolfin.read_checkpoint(h2, name, 0)["values"]
+        assert np.linalg.norm(a - b) <= 1e-12 * np.linalg.norm(a), name

@@ -266,6 +266,8 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
     if shard_file is not None:
         shard_file.flush()
         del shard_file
+    if comm is not None:
+        comm.barrier()  # every rank's WSS block is on disk before rank 0 starts merging them
     # the single collective (15*nF partial sums + the snapshot count) happens below, fused with the final formulas
 
     if rank == 0:
@@ -283,6 +285,8 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
         print("=" * 10, "Saving hemodynamic indices", "=" * 10)
 
     out = comm.reduce_finalize(n_snap) if comm is not None else eng.finalize(n_snap)
+    if comm is not None:
+        comm.close()  # ranks > 0 are done here; rank 0 goes on to write the index files
     timers = eng.timers()
     series.close()
     if rank == 0:

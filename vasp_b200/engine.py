@@ -297,6 +297,10 @@ class HemoEngine:
     def barrier(self) -> None:
         check(self._lib.vh_nccl_barrier(self._h))
 
+    def nccl_destroy(self) -> None:
+        """Unmap the peers' memory and destroy the communicator (collective in practice: see NcclComm.close)."""
+        check(self._lib.vh_nccl_destroy(self._h))
+
     def peer_init(self) -> None:
         """Map every rank's running sums over NVLink (CUDA IPC); collective, after ``nccl_init``."""
         check(self._lib.vh_peer_init(self._h))
