@@ -15,6 +15,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --c
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-io-leg > $OUT/launches_bench.log 2>&1; echo "launches rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k2_wall|k1_stage|k3_fold' -s 12 -c 3 \
     -f -o $OUT/prof_stenosis_p1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-io-leg > $OUT/ncu_stenosis_p1.log 2>&1; echo "ncu rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k2_wall|k1_stage' -s 12 -c 2 \
-    -f -o $OUT/prof_stenosis_p2 python bench.py --workload stenosis_p2 --steps 2 --warmup 3 --no-cpu-baseline --no-io-leg > $OUT/ncu_stenosis_p2.log 2>&1; echo "ncu p2 rc=$?"
 cat $OUT/bench_stenosis_p1.json
