@@ -204,3 +204,39 @@ def test_cli_flag_set_and_error_conventions(tmp_path, monkeypatch):
         ch.main(["--folder", str(tmp_path)])
     assert ch.compute_hemodynamics is ch.compute_hemodyanamics
     assert ch.read_parameters_from_file(tmp_path) == {"save_deg": 2, "mu_f": 1.0}
+
+
+def test_rank_and_world_from_mpi_and_slurm_launchers(monkeypatch):
+    """The reference is started with `mpirun -np N vasp-compute-hemo` (docs/postprocess.md:165); the same command line
+    must find its rank without mpi4py: Open MPI, MPICH/hydra and srun variables, torchrun's taking precedence."""
+    from vasp_b200 import timeshard
+    names = [n for trio in timeshard._LAUNCHERS for n in trio] + ["PMIX_NAMESPACE", "SLURM_JOB_ID", "SLURM_STEP_ID",
+                                                                 "OMPI_MCA_ess_base_jobid", "PMI_JOBID",
+                                                                 "TORCHELASTIC_RUN_ID", "MASTER_PORT"]
+    for n in names:
+        monkeypatch.delenv(n, raising=False)
+    assert timeshard.env_rank_world() == (0, 0, 1)
+    plain = timeshard._rendezvous_path(2, "/tmp")
+    monkeypatch.setenv("OMPI_COMM_WORLD_RANK", "3")
+    monkeypatch.setenv("OMPI_COMM_WORLD_SIZE", "8")
+    monkeypatch.setenv("OMPI_COMM_WORLD_LOCAL_RANK", "1")
+    assert timeshard.env_rank_world() == (3, 1, 8)
+    monkeypatch.setenv("PMIX_NAMESPACE", "prterun-node-123@1")
+    a = timeshard._rendezvous_path(8, "/tmp")
+    assert "prterun-node-123@1" in a.name and a != plain
+    monkeypatch.setenv("SLURM_PROCID", "5")
+    monkeypatch.setenv("SLURM_NTASKS", "6")
+    assert timeshard.env_rank_world() == (3, 1, 8)            # first launcher in the table wins
+    for n in ("OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_RANK", "PMIX_NAMESPACE"):
+        monkeypatch.delenv(n)
+    assert timeshard.env_rank_world() == (5, 5, 6)            # no local id given: the rank itself
+    monkeypatch.setenv("SLURM_JOB_ID", "77")
+    monkeypatch.setenv("SLURM_STEP_ID", "0")
+    assert timeshard._rendezvous_path(6, "/tmp").name == "vasp_b200_nccl_0_77_0_6.id"
+    monkeypatch.setenv("PMI_RANK", "1")
+    monkeypatch.setenv("PMI_SIZE", "2")
+    assert timeshard.env_rank_world() == (1, 1, 2)
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("WORLD_SIZE", "4")
+    monkeypatch.setenv("LOCAL_RANK", "0")
+    assert timeshard.env_rank_world() == (0, 0, 4)            # torchrun's contract first

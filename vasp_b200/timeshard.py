@@ -22,12 +22,33 @@ import numpy as np
 from ._lib import PUSH_GLOBAL_FIRST, PUSH_HALO_FIRST
 
 
+# (rank, world size, local rank) variables of the launchers a VaSP user may start the tool with: torchrun's contract
+# first, then Open MPI (the reference is run as `mpirun -np N vasp-compute-hemo`, docs/postprocess.md:165), MPICH /
+# Intel MPI (hydra), Slurm's srun.  mpi4py is not needed: the ranks only have to know who they are.
+_LAUNCHERS = (
+    ("RANK", "WORLD_SIZE", "LOCAL_RANK"),
+    ("OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_RANK"),
+    ("PMI_RANK", "PMI_SIZE", "MPI_LOCALRANKID"),
+    ("SLURM_PROCID", "SLURM_NTASKS", "SLURM_LOCALID"),
+)
+
+
 def env_rank_world() -> Tuple[int, int, int]:
     """(rank, local_rank, world_size) from the launcher's environment; (0, 0, 1) when run plainly."""
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", str(rank)))
-    return rank, local, world
+    for r, w, l in _LAUNCHERS:
+        if r in os.environ and w in os.environ:
+            rank, world = int(os.environ[r]), int(os.environ[w])
+            return rank, int(os.environ.get(l, str(rank))), world
+    return 0, 0, 1
+
+
+def _job_tag() -> str:
+    """Something all ranks of one job share and no other job has (names the rendezvous file of the NCCL id)."""
+    for names in (("PMIX_NAMESPACE",), ("OMPI_MCA_ess_base_jobid",), ("PMI_JOBID",), ("SLURM_JOB_ID", "SLURM_STEP_ID")):
+        if all(n in os.environ for n in names):
+            return "_".join(os.environ[n] for n in names).replace("/", "-")
+    # torchrun and plain subprocess launchers: all workers share their parent process
+    return f"{os.getppid()}_{os.environ.get('TORCHELASTIC_RUN_ID', 'none')}"
 
 
 @dataclass(frozen=True)
@@ -107,9 +128,7 @@ def exchange_unique_id(rank: int, world: int, make_id: Callable[[], bytes], time
     The file name carries the launcher's pid (all workers of one torchrun share their parent) and MASTER_PORT, so
     concurrent or consecutive jobs cannot pick up each other's id; rank 0 removes any stale file first and every
     rank checks a nonce made of the launcher pid and start time."""
-    tag = f"{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}_{os.environ.get('TORCHELASTIC_RUN_ID', 'none')}"
-    d = Path(directory or os.environ.get("VASP_B200_RDZV_DIR", "/tmp"))
-    path = d / f"vasp_b200_nccl_{tag}_{world}.id"
+    path = _rendezvous_path(world, directory)
     if rank == 0:
         uid = make_id()
         tmp = path.with_suffix(f".tmp{os.getpid()}")
@@ -130,6 +149,12 @@ def exchange_unique_id(rank: int, world: int, make_id: Callable[[], bytes], time
     raise TimeoutError(f"rank {rank}: NCCL unique id file {path} did not appear within {timeout}s")
 
 
+def _rendezvous_path(world: int, directory: Optional[str] = None) -> Path:
+    tag = f"{os.environ.get('MASTER_PORT', '0')}_{_job_tag()}"
+    d = Path(directory or os.environ.get("VASP_B200_RDZV_DIR", "/tmp"))
+    return d / f"vasp_b200_nccl_{tag}_{world}.id"
+
+
 def _process_start_time() -> float:
     try:
         return os.stat(f"/proc/{os.getpid()}").st_ctime
@@ -138,10 +163,8 @@ def _process_start_time() -> float:
 
 
 def cleanup_unique_id(world: int, directory: Optional[str] = None) -> None:
-    tag = f"{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}_{os.environ.get('TORCHELASTIC_RUN_ID', 'none')}"
-    d = Path(directory or os.environ.get("VASP_B200_RDZV_DIR", "/tmp"))
     try:
-        (d / f"vasp_b200_nccl_{tag}_{world}.id").unlink()
+        _rendezvous_path(world, directory).unlink()
     except FileNotFoundError:
         pass
 
