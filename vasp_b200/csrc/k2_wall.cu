@@ -893,7 +893,10 @@ int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_el
     const int gx_multi = (int)((n_multi + K2_WARPS - 1) / K2_WARPS);
     // (facet, segment) warps per launch: a few waves of the resident warps, so that the tail is short and the
     // prologue (three dependent loads) of one warp hides behind the passes of the others
-    static const int64_t waves = env_int("VASP_B200_K2_WAVES", 2);
+    // measured (headline mesh, 1000 snapshots): P1 step 53.3 / 56.2 / 60.4 us at 1 / 2 / 3 waves (K2 itself is flat, every
+    // extra segment costs K3), P2 255 / 248 / 251 us
+    static const int64_t waves_env = env_int("VASP_B200_K2_WAVES", 0);
+    const int64_t waves = waves_env > 0 ? waves_env : (h->order == 1 ? 1 : 2);
     int64_t pos = 0;
     while (pos < n_snap) {
         const int halo = (pos == 0 && prev_mode == 2) ? 1 : 0;
