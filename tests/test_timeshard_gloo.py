@@ -107,3 +107,60 @@ def test_unique_id_exchange_through_a_file(tmp_path, monkeypatch):
     assert got0 == got1 == uid
     timeshard.cleanup_unique_id(2, directory=str(tmp_path))
     assert not list(tmp_path.iterdir())
+
+
+CLI_WORKER = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, os.environ["REPO_ROOT"])
+import torch.distributed as dist
+from tests.fake_engine import OracleHemoEngine
+from vasp_b200 import compute_hemodynamics as ch, engine as engine_mod, timeshard
+
+dist.init_process_group("gloo")
+ch.HemoEngine = OracleHemoEngine
+ch.pinned_empty = engine_mod.pinned_empty = lambda shape: np.zeros(shape)
+ch.NcclComm = lambda eng, rank, world: timeshard.TorchDistComm(eng)
+ch.main(["--folder", os.environ["FOLDER"]])
+dist.destroy_process_group()
+'''
+
+
+def test_entry_point_under_two_ranks_merges_the_wss_series(tmp_path):
+    """The multi-rank plumbing of the entry point on CPU (stand-in engine, gloo communicator): time shards with a halo
+    snapshot, per-rank WSS blocks merged by rank 0 after a barrier, one reduction -- same six files as one rank."""
+    import shutil
+    from tests.test_gpu_cli import _make_folder
+    from tests.test_cli_host_logic import _u_syn
+    from vasp_b200 import io_dolfin
+    one, two = tmp_path / "one", tmp_path / "two"
+    one.mkdir()
+    _make_folder(one, _u_syn(9), 11, 0.04, 3.5e-3)
+    shutil.copytree(one, two)
+    port = _free_port()
+
+    def launch(folder, world):
+        procs = []
+        for rank in range(world):
+            env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                       MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port + world), REPO_ROOT=str(ROOT), FOLDER=str(folder),
+                       OMP_NUM_THREADS="1")
+            procs.append(subprocess.Popen([sys.executable, "-c", CLI_WORKER], env=env, stdout=subprocess.PIPE,
+                                          stderr=subprocess.STDOUT, text=True))
+        outs = [p.communicate(timeout=600)[0] for p in procs]
+        for p, o in zip(procs, outs):
+            assert p.returncode == 0, o
+        return outs
+
+    launch(one, 1)
+    outs = launch(two, 2)
+    assert "Calculating WSS at Timestep" in outs[0] and "Calculating WSS at Timestep" not in outs[1]
+    h1, h2 = one / "Hemodynamic_indices", two / "Hemodynamic_indices"
+    assert sorted(f.name for f in h2.iterdir()) == sorted(f.name for f in h1.iterdir())   # no shard files left behind
+    for k in range(11):
+        a, b = io_dolfin.read_checkpoint(h1, "WSS", k), io_dolfin.read_checkpoint(h2, "WSS", k)
+        assert np.array_equal(a["values"], b["values"]), k
+    assert (h1 / "WSS.xdmf").read_text() == (h2 / "WSS.xdmf").read_text()
+    for name in ("TAWSS", "OSI", "RRT", "ECAP", "TWSSG"):
+        a, b = io_dolfin.read_checkpoint(h1, name, 0)["values"], io_dolfin.read_checkpoint(h2, name, 0)["values"]
+        assert np.linalg.norm(a - b) <= 1e-12 * np.linalg.norm(a), name

@@ -244,6 +244,11 @@ class TorchDistComm:
         out = t.numpy()
         self.engine.set_sums(out[:-1].reshape(sums.shape), int(round(out[-1])))
 
+    def reduce_finalize(self, n_total: int, host: bool = True):
+        """Same contract as :meth:`NcclComm.reduce_finalize`: global indices on every rank."""
+        self.allreduce_sums()
+        return self.engine.finalize(n_total)
+
     def max(self, value: float) -> float:
         import torch
         t = torch.tensor([float(value)], dtype=torch.float64)
