@@ -1,13 +1,18 @@
 #!/usr/bin/env python
 """Benchmark of the wall-shear-stress hot path (BASELINE.json metric: wall-facet x snapshots / s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] [--snapshots S]
+                    [--wss none|steps|matrix] [--no-cpu-baseline] [--no-io-leg]
 
-One *step* is one pass of the whole hot path over the workload's snapshot batch: zero the running sums, per-snapshot
-traction + time reductions for every snapshot (K2/K3), the NCCL all-reduce of the partial sums when N > 1, and the
-final TAWSS/OSI/RRT/ECAP/TWSSG formulas (K4).  ``value`` times that with the snapshots already resident in HBM (CUDA
-events on the launching stream, L2 flushed between steps); ``e2e`` times the same pass through the public Python/C
-ABI call with pinned HOST snapshots (H2D inside) and the D2H read of the five result fields.
+One *step* is one pass of the whole hot path over the workload's snapshot batch: staging (K1), per-snapshot traction +
+time reductions (K2), fold of the segments + the final TAWSS/OSI/RRT/ECAP/TWSSG formulas (K3; the first fold of a time
+loop overwrites the running sums), and -- when N > 1 -- the fused peer-memory reduction + final formulas over NVLink
+(or ncclAllReduce + K4).  ``value`` times that with the snapshots already resident in HBM: CUDA events on the compute
+stream around EXACTLY K steps, rotating over resident input copies larger than L2, no events between the kernels;
+the same K steps then run once more with events around K1 and K2 for the per-launch durations of ``roofline``.
+``e2e`` times the same pass through the public Python/C-ABI call with pinned HOST snapshots (H2D inside) and the D2H
+read of the five result fields.  ``cpu_baseline`` is the restated reference algorithm (C oracle) on the host cores,
+``io`` the HDF5 -> device path of the entry point timed apart (cold / warm page cache) plus the whole entry point.
 
 Under ``torch.distributed.run`` (N > 1) every rank drives one GPU on its own contiguous time range (weak scaling:
 each rank processes the workload's snapshot count) and rank 0 prints the single JSON line.  No torch is imported.
