@@ -212,7 +212,7 @@ def test_rank_and_world_from_mpi_and_slurm_launchers(monkeypatch):
     from vasp_b200 import timeshard
     names = [n for trio in timeshard._LAUNCHERS for n in trio] + ["PMIX_NAMESPACE", "SLURM_JOB_ID", "SLURM_STEP_ID",
                                                                  "OMPI_MCA_ess_base_jobid", "PMI_JOBID",
-                                                                 "TORCHELASTIC_RUN_ID", "MASTER_PORT"]
+                                                                 "TORCHELASTIC_RUN_ID", "MASTER_PORT", "SLURM_NTASKS"]
     for n in names:
         monkeypatch.delenv(n, raising=False)
     assert timeshard.env_rank_world() == (0, 0, 1)
@@ -226,10 +226,14 @@ def test_rank_and_world_from_mpi_and_slurm_launchers(monkeypatch):
     assert "prterun-node-123@1" in a.name and a != plain
     monkeypatch.setenv("SLURM_PROCID", "5")
     monkeypatch.setenv("SLURM_NTASKS", "6")
+    monkeypatch.setenv("SLURM_STEP_NUM_TASKS", "6")
     assert timeshard.env_rank_world() == (3, 1, 8)            # first launcher in the table wins
     for n in ("OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_RANK", "PMIX_NAMESPACE"):
         monkeypatch.delenv(n)
     assert timeshard.env_rank_world() == (5, 5, 6)            # no local id given: the rank itself
+    monkeypatch.delenv("SLURM_STEP_NUM_TASKS")
+    assert timeshard.env_rank_world() == (0, 0, 1)            # batch-script environment (no srun step): a plain run
+    monkeypatch.setenv("SLURM_STEP_NUM_TASKS", "6")
     monkeypatch.setenv("SLURM_JOB_ID", "77")
     monkeypatch.setenv("SLURM_STEP_ID", "0")
     assert timeshard._rendezvous_path(6, "/tmp").name == "vasp_b200_nccl_0_77_0_6.id"

@@ -29,7 +29,9 @@ _LAUNCHERS = (
     ("RANK", "WORLD_SIZE", "LOCAL_RANK"),
     ("OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_RANK"),
     ("PMI_RANK", "PMI_SIZE", "MPI_LOCALRANKID"),
-    ("SLURM_PROCID", "SLURM_NTASKS", "SLURM_LOCALID"),
+    # srun only: SLURM_STEP_NUM_TASKS exists inside a job step, not in the batch script's own environment (where
+    # SLURM_NTASKS = n would make a single plain process wait for n - 1 ranks that never start)
+    ("SLURM_PROCID", "SLURM_STEP_NUM_TASKS", "SLURM_LOCALID"),
 )
 
 
