@@ -23,6 +23,7 @@ import argparse
 import json
 import logging
 import os
+import queue
 import threading
 import time
 from concurrent.futures import ThreadPoolExecutor
@@ -71,6 +72,55 @@ def read_parameters_from_file(folder: Union[str, Path]) -> Optional[Dict]:
     except json.JSONDecodeError as e:
         logging.error(f"Error parsing JSON file: {e}")
         return None
+
+
+class _Drain:
+    """One worker thread that stores finished WSS blocks in submission order while the caller computes the next
+    one; ``wait_free(slot)`` blocks until the block last submitted from ``slot`` has been stored."""
+
+    def __init__(self, store):
+        self._store, self.seconds = store, 0.0
+        self._q: "queue.Queue" = queue.Queue()
+        self._free = [threading.Event(), threading.Event()]
+        for e in self._free:
+            e.set()
+        self._error: Optional[BaseException] = None
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _run(self) -> None:
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            slot, buf, first_step, n_steps = item
+            try:
+                if self._error is None:
+                    t0 = time.perf_counter()
+                    self._store(buf, first_step, n_steps)
+                    self.seconds += time.perf_counter() - t0
+            except BaseException as e:  # surfaced in the caller
+                self._error = e
+            finally:
+                self._free[slot].set()
+
+    def _check(self) -> None:
+        if self._error is not None:
+            raise self._error
+
+    def wait_free(self, slot: int) -> None:
+        self._free[slot].wait()
+        self._check()
+
+    def submit(self, slot: int, buf, first_step: int, n_steps: int) -> None:
+        self._check()
+        self._free[slot].clear()
+        self._q.put((slot, buf, first_step, n_steps))
+
+    def close(self) -> None:
+        self._q.put(None)
+        self._thread.join()
+        self._check()
 
 
 def default_block_snapshots(vec_len: int) -> int:
@@ -233,30 +283,41 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
     reader = _BlockReader(series, shard.read_start, shard.stop, block_snapshots)
     first, done = True, 0
     t_setup = time.perf_counter() - t_begin
-    t_push = t_write = 0.0
-    for a, b, u in reader:
-        flags = shard.first_push_flags() if first else 0
-        n_real = (b - a) - (1 if (first and shard.has_halo) else 0)
-        t0 = time.perf_counter()
-        if direct is not None:
-            m = eng.push(u, flags=flags)  # columns [done, done + n_real) of the time-major matrix
-            wss_buf = np.ascontiguousarray(m[:, done:done + n_real].T).reshape(n_real, nF, 3, 3)
-        else:
-            eng.push(u, flags=flags, wss_out=wss_buf)
-        t1 = time.perf_counter()
-        t_push += t1 - t0
-        for r in range(n_real):
-            k = shard.start + done + r
+    t_push = 0.0
+
+    # The WSS steps of block i are written (WSS.h5 on rank 0, the shard file elsewhere) by a thread while block i + 1
+    # is on the GPU: two result buffers, one being filled by the push, one being drained.
+    def store(buf, first_step, n_steps):
+        for r in range(n_steps):
+            k = shard.start + first_step + r
             t = float(series.timestamps[k])
             if rank == 0:
                 print("=" * 10, f"Calculating WSS at Timestep: {t}", "=" * 10)
                 # Write temporal WSS
-                wss_writer.write(wss_buf[r], t)
+                wss_writer.write(buf[r], t)
             else:
-                shard_file[done + r] = wss_buf[r]
-        t_write += time.perf_counter() - t1
+                shard_file[first_step + r] = buf[r]
+
+    drain = _Drain(store)
+    wss_bufs = [wss_buf, pinned_empty(wss_buf.shape)] if wss_buf is not None else [None, None]
+    for i, (a, b, u) in enumerate(reader):
+        flags = shard.first_push_flags() if first else 0
+        n_real = (b - a) - (1 if (first and shard.has_halo) else 0)
+        slot = i & 1
+        drain.wait_free(slot)  # the block written two pushes ago has left this buffer
+        t0 = time.perf_counter()
+        if direct is not None:
+            m = eng.push(u, flags=flags)  # columns [done, done + n_real) of the time-major matrix
+            out_block = np.ascontiguousarray(m[:, done:done + n_real].T).reshape(n_real, nF, 3, 3)
+        else:
+            eng.push(u, flags=flags, wss_out=wss_bufs[slot])
+            out_block = wss_bufs[slot]
+        t_push += time.perf_counter() - t0
+        drain.submit(slot, out_block, done, n_real)
         done += n_real
         first = False
+    drain.close()
+    t_write = drain.seconds
     series_io = reader.io_seconds
     if direct is not None:
         direct.detach()
