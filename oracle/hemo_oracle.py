@@ -8,7 +8,12 @@ PARITY UNPINNED at the 1e-10 level: the reference evaluates this path inside leg
 (dolfin/FFC/FIAT/PETSc), none of which is installable here, and the reference's own input blobs for its
 single test are not shipped (``.MISSING_LARGE_BLOBS``).  What *is* pinned: the reference test's known answer
 (``tests/test_compute_hemodynamics.py:68-73``: wall-averaged TAWSS of Poiseuille flow in (1.95, 2.05)) and its
-OSI range assertion (``:84-88``, ``compute_hemodynamics.py:366-372``); see ``tests/test_oracle.py``.
+OSI range assertion (``:84-88``, ``compute_hemodynamics.py:366-372``); see ``tests/test_oracle.py``.  Also pinned, by
+RUNNING the reference's own Python in the build container (``tests/golden/make_reference_goldens.py`` ->
+``tests/test_reference_goldens.py``): the dof copy map against ``InterpolateDG.__call__`` (``:65-89``) and the whole
+time-loop bookkeeping against ``compute_hemodyanamics`` (``:160-372``) executed on emulated dolfin objects, with only
+``Stress`` and ``project_dg`` standing on this file's restatements.  Still unpinned: the finite-element assembly
+inside dolfin/FFC (facet quadrature, the 7-point rule of ``project_dg``) and dolfin's boundary-mesh numbering.
 
 The restatement is deliberately *literal*: it assembles the same facet integrals dolfin would assemble, with the
 quadrature rules FFC would pick, solves the same block systems and re-does the reference's coordinate-matching

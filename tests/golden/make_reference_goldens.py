@@ -19,7 +19,14 @@ args  ``parse_arguments`` (postprocessing_fenics_common.py:10-28)              `
 par   ``read_parameters_from_file`` (postprocessing_common.py:124-145)         ``compute_hemodynamics.read_parameters_...``
 ctm   ``create_transformed_matrix(quantity="wss")``                            ``wss_matrix.create_transformed_matrix_wss``
       (postprocessing_h5py_common.py:154-407)
+idg   ``InterpolateDG.__call__`` (compute_hemodynamics.py:65-89): the          ``oracle.hemo_oracle`` ``bcell_local`` (R5), which
+      coordinate-matching dof copy from the cell to the boundary space        the CUDA precompute must reproduce bit-exactly
 ====  =====================================================================  ==========================================
+
+``idg`` runs the method of the real class on an instance whose dolfin-typed attributes are replaced by small numpy-backed
+objects (dof coordinates, cell dofs, facet -> cell, sub-space dofmaps): the loop, its ``np.allclose`` test and its
+first-match ``break`` are the reference's; the dof numbering handed to it (cell-major DG1, 3 dofs per boundary cell) is
+this repository's reading of dolfin's and does not influence *which* cell dof a boundary dof is matched to.
 
 Inputs are small synthetic files written with this repository's writers (stored in the fixture so the tests can
 re-create them byte for byte) plus the reference's own test meshes (``tests/test_data/*``, domain tables only).
@@ -55,10 +62,26 @@ def install_shims() -> None:
 
     h5py.File = File
     sys.modules["h5py"] = h5py
-    for name in ("matplotlib", "matplotlib.pyplot", "dolfin"):
+    for name in ("matplotlib", "matplotlib.pyplot", "mpi4py", "petsc4py", "vampy", "vampy.automatedPostprocessing",
+                 "vampy.automatedPostprocessing.postprocessing_common"):
         sys.modules[name] = types.ModuleType(name)
-    for n in ("TestFunction", "TrialFunction", "inner", "Function", "LocalSolver", "dx", "FunctionSpace"):
-        setattr(sys.modules["dolfin"], n, None)  # imported by name at postprocessing_fenics_common.py:7, never called
+    sys.modules["mpi4py"].MPI = sys.modules["petsc4py"].PETSc = None
+    sys.modules["vampy.automatedPostprocessing.postprocessing_common"].get_dataset_names = None
+
+    class _Params(dict):  # dolfin.parameters["form_compiler"]["quadrature_degree"] = ... at import time
+        def __missing__(self, key):
+            self[key] = _Params()
+            return self[key]
+
+    class _Dolfin(types.ModuleType):  # every dolfin name is importable; none of them is called by what runs here
+        parameters = _Params()
+
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return None
+
+    sys.modules["dolfin"] = _Dolfin("dolfin")
     # namespace stubs: the package __init__ files import every sibling tool (matplotlib, vmtk, ...)
     for dotted in ("vasp", "vasp.postprocessing", "vasp.postprocessing.postprocessing_fenics",
                    "vasp.postprocessing.postprocessing_h5py"):
@@ -115,6 +138,209 @@ def write_wss_case(folder: Path, vals: np.ndarray, times, btopo, bgeom) -> None:
     for v, t in zip(vals, times):
         m.write(np.linalg.norm(v, axis=2), t)
     m.close()
+
+
+def run_reference_time_loop(rc) -> dict:
+    """Execute ``compute_hemodyanamics`` of the reference (compute_hemodynamics.py:160-372) line by line.
+
+    dolfin is absent, so the names the function uses are bound to small numpy-backed stand-ins: vectors with
+    ``[:]`` / ``get_local`` / ``set_local`` / ``axpy`` / ``zero``, function spaces that only know their sizes, an
+    ``HDF5File`` that reads the real ``u.h5`` through h5lite, an ``XDMFFile`` that records what is written.  The two
+    finite-element pieces -- ``Stress`` (:120-157) and ``project_dg`` (postprocessing_fenics_common.py:31-54) -- are
+    replaced by the oracle's restatements (they need an assembler).  Everything else is the reference's own code: which
+    snapshots are read, ``dt``, ``tau_prev = 0`` at the first step, the magnitude via ``reshape(local_size, block_size)``
+    and ``np.linalg.norm``, the accumulations, the division by ``counter``, RRT / OSI / ECAP, the OSI assertion, the
+    order and time stamps of the ``WSS`` checkpoints.  Vector functions use dolfin's node-interleaved layout (dof
+    ``3 n + c``), which is what the reference's own reshape assumes."""
+    from oracle import hemo_oracle as ho
+    from vasp_b200 import synth
+    from vasp_b200.io_dolfin import get_dataset_names
+    meshes = np.load(HERE / "fluid_meshes.npz")
+    xyz, tets = meshes["cylinder_xyz"], meshes["cylinder_tets"].astype(np.int64)
+    rx, rt = synth.refine_uniform(xyz, tets, seed=3)
+    n = len(rx)
+    n_snap, dt, mu, stride = 9, 0.02, 0.0035, 2
+    basis = synth.velocity_basis(rx, seed=6)
+    times = [dt * (k + 1) for k in range(n_snap)]
+    coef = np.array([[1 + 0.6 * np.sin(40 * t), 0.2 * np.sin(70 * t + 1), 0.1 * np.cos(90 * t), 0.3 * np.sin(30 * t + 2)]
+                     for t in times])
+    vecs = synth.velocity_series(basis, coef)
+    node_of_p2 = ho.match_points(ho.p2_node_coordinates(xyz, ho.p2_cell_nodes(tets)[1]), rx, 1e-9)
+    S = ho.SurfaceStress(xyz, tets, mu, 2, node_of_p2)
+    nF = S.nF
+    rec = {"checkpoints": []}
+
+    class Vec:
+        def __init__(self, n_):
+            self.a = np.zeros(n_)
+
+        def __getitem__(self, idx):
+            return self.a[idx].copy()
+
+        def __setitem__(self, idx, val):
+            self.a[idx] = val.a if isinstance(val, Vec) else val
+
+        def get_local(self):
+            return self.a.copy()
+
+        def set_local(self, v):
+            self.a[:] = v
+
+        def apply(self, mode):
+            pass
+
+        def axpy(self, alpha, other):
+            self.a += alpha * other.a
+
+        def zero(self):
+            self.a[:] = 0.0
+
+    class Space:
+        def __init__(self, kind, size, vector):
+            self.kind, self.size, self.vector = kind, size, vector
+
+        def num_sub_spaces(self):
+            return 3 if self.vector else 0
+
+        def dofmap(self):
+            return types.SimpleNamespace(block_size=lambda: 3 if self.vector else 1)
+
+        def sub(self, i):
+            return types.SimpleNamespace(collapse=lambda: Space(self.kind + "_sub", self.size // 3, False), index=i,
+                                         parent=self)
+
+    class Fn:
+        def __init__(self, space):
+            self.space, self.v = space, Vec(space.size)
+
+        def vector(self):
+            return self.v
+
+        def rename(self, a, b):
+            self.name = a
+
+        def sub(self, i):
+            return ("component", self, i)
+
+    class Assigner:
+        def __init__(self, to_space, from_sub):
+            pass
+
+        def assign(self, target, source):
+            _, f, i = source
+            target.v.a[:] = f.v.a[i::3]
+
+    class H5:
+        def __init__(self, comm, path, mode):
+            self.f = H5File(path)
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            self.f.close()
+
+        def close(self):
+            self.f.close()
+
+        def read(self, target, name, *flags):
+            if isinstance(target, Fn):
+                target.v.a[:] = self.f[name.lstrip("/")].read().ravel()
+
+        def attributes(self, name):
+            return {k: (float(v) if np.ndim(v) == 0 else v) for k, v in self.f[name.lstrip("/")].attrs.items()}
+
+    class Xdmf:
+        Encoding = types.SimpleNamespace(HDF5="HDF5")
+
+        def __init__(self, comm, path):
+            self.parameters, self.name = {}, Path(path).stem
+
+        def write_checkpoint(self, f, name, t, enc, append=False):
+            rec["checkpoints"].append((self.name, name, float(t), bool(append), f.v.get_local()))
+
+        def close(self):
+            pass
+
+    class StressStandIn:  # Stress(u=u_p2, ...): the oracle's restatement of :120-157, evaluated on u's current vector
+        def __init__(self, u, V_dg, V_sub, mu_f, mesh, boundary_mesh):
+            assert mu_f == mu
+            self.u, self.out = u, Fn(V_sub)
+
+        def __call__(self):
+            self.out.v.a[:] = S(self.u.v.a, (0, n, 2 * n)).reshape(-1)
+            return self.out
+
+    class Pow:  # inner(twssg, twssg) ** (1 / 2)
+        def __init__(self, f):
+            self.f = f
+
+        def __pow__(self, e):
+            assert e == 0.5
+            return self
+
+    def project_dg_stand_in(expr, V):  # postprocessing_fenics_common.py:31-54 through the oracle's restatement
+        g = Fn(V)
+        g.v.a[:] = ho.project_dg_norm(expr.f.v.a.reshape(nF, 3, 3), S.area).reshape(-1)
+        return g
+
+    def names(f, step=1, vector_filename="/velocity/vector_%d"):  # VaMPy's get_dataset_names: not in the reference tree
+        return ["/velocity/" + x for x in get_dataset_names(f.f["velocity"], step=step)]
+
+    spaces = {"CG1": Space("CG1", 3 * n, True), "CG2": Space("CG2", 3 * n, True), "DGb3": Space("DGb3", 9 * nF, True),
+              "DGb1": Space("DGb1", 3 * nF, False), "DG3": Space("DG3", 12 * len(tets), True)}
+
+    def vfs(mesh, fam, deg):
+        return spaces[{("refined", "CG", 1): "CG1", ("mesh", "CG", 2): "CG2", ("bmesh", "DG", 1): "DGb3",
+                       ("mesh", "DG", 1): "DG3"}[(mesh.tag, fam, deg)]]
+
+    mesh_objs = iter([types.SimpleNamespace(tag="mesh"), types.SimpleNamespace(tag="refined")])
+    rc.Mesh = lambda: next(mesh_objs)
+    rc.BoundaryMesh = lambda mesh, kind: types.SimpleNamespace(tag="bmesh")
+    rc.VectorFunctionSpace = vfs
+    rc.FunctionSpace = lambda mesh, fam, deg: spaces["DGb1"]
+    rc.Function = Fn
+    rc.HDF5File = H5
+    rc.XDMFFile = Xdmf
+    rc.MPI = types.SimpleNamespace(comm_world=None, rank=lambda comm: 0)
+    rc.PETScDMCollection = types.SimpleNamespace(
+        create_transfer_matrix=lambda a, b: types.SimpleNamespace(__mul__=None))
+
+    class Transfer:  # R2: for nested meshes the transfer matrix is a permutation; the node map lives in the stand-in above
+        def __mul__(self, vec):
+            return vec.get_local()
+
+    rc.PETScDMCollection = types.SimpleNamespace(create_transfer_matrix=lambda a, b: Transfer())
+    rc.FunctionAssigner = Assigner
+    rc.Stress = StressStandIn
+    rc.project_dg = project_dg_stand_in
+    rc.inner = lambda a, b: Pow(a)
+    rc.get_dataset_names = names
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        (td / "Mesh").mkdir()
+        (td / "Visualization_separate_domain").mkdir()
+        for nm in ("mesh.h5", "mesh_fluid.h5"):
+            io_dolfin.write_mesh(td / "Mesh" / nm, xyz, tets)
+        io_dolfin.write_mesh(td / "Mesh" / "mesh_refined_fluid.h5", rx, rt)
+        io_dolfin.write_velocity_series(td / "Visualization_separate_domain" / "u.h5", rt, n, vecs, times)
+        with redirect_stdout(io.StringIO()) as log:
+            rc.compute_hemodyanamics(td / "Visualization_separate_domain", td / "Mesh" / "mesh.h5", mu, stride)
+        assert (td / "Hemodynamic_indices").is_dir()
+    cps = rec["checkpoints"]
+    wss = [c for c in cps if c[0] == "WSS"]
+    res = {"loop_seed": np.array(json.dumps({"mesh": "cylinder", "refine_seed": 3, "basis_seed": 6, "n_snap": n_snap,
+                                             "dt": dt, "mu": mu, "stride": stride})),
+           "loop_coef": coef, "loop_stdout": np.array(log.getvalue()),
+           "loop_wss_times": np.array([c[2] for c in wss]), "loop_wss_append": np.array([c[3] for c in wss]),
+           "loop_wss": np.stack([c[4] for c in wss])}
+    for c in cps:
+        if c[0] != "WSS":
+            assert c[0] == c[1] and c[2] == 0.0 and c[3] is False
+            res["loop_" + c[0]] = c[4]
+    assert sorted(k for k in res if k.startswith("loop_") and k[5:].isupper()) == \
+        ["loop_ECAP", "loop_OSI", "loop_RRT", "loop_TAWSS", "loop_TWSSG"]
+    return res
 
 
 def main() -> None:
@@ -177,6 +403,59 @@ def main() -> None:
             out[f"ids_{name}_domains"] = h["domains/values"].read().ravel().astype(np.int32)
             out[f"ids_{name}_topology"] = h["domains/topology"].read().astype(np.int32)
         out[f"ids_{name}_query"] = np.array(json.dumps([fid, sid]))
+    # ---- idg: the reference's InterpolateDG.__call__ on duck-typed spaces
+    rc = importlib.import_module("vasp.postprocessing.postprocessing_fenics.compute_hemodynamics")
+    from oracle import hemo_oracle as ho
+    meshes = np.load(HERE / "fluid_meshes.npz")
+    for name in ("cylinder", "stenosis"):
+        xyz, tets = meshes[f"{name}_xyz"], meshes[f"{name}_tets"].astype(np.int64)
+        S = ho.SurfaceStress(xyz, tets, 1.0, 1)
+        m, cells = S.maps, S.tets                      # cells: vertices ascending, as dolfin orders them
+        nF, nc = S.nF, len(cells)
+
+        class _Sub:  # V.sub(k)
+            def __init__(self, k):
+                self.k = k
+
+            def dofmap(self):
+                return self
+
+            def entity_closure_dofs(self, mesh, dim, entities):
+                assert dim == 3 and len(entities) == 1
+                return np.array([12 * entities[0] + 4 * self.k + v for v in range(4)])
+
+        class _SubDofmap:  # dofmap of a collapsed scalar DG1 space on the boundary mesh
+            def cell_dofs(self, i):
+                return np.array([3 * i, 3 * i + 1, 3 * i + 2])
+
+        class _Vec:
+            def __init__(self, store, k):
+                self.store, self.k = store, k
+
+            def vector(self):
+                return self
+
+            def set_local(self, v):
+                self.store[self.k] = np.array(v)
+
+        got = {}
+        idg = rc.InterpolateDG.__new__(rc.InterpolateDG)
+        idg.V = types.SimpleNamespace(sub=lambda k: _Sub(k))
+        idg.mesh = types.SimpleNamespace(topology=lambda: types.SimpleNamespace(dim=lambda: 3))
+        idg.sub_map = np.arange(nF)                                        # boundary cell i <-> facet i
+        idg.f_to_c = lambda facet: np.array([m.facet_cell[facet]])
+        idg.sub_coords = [xyz[m.bcell_parent].reshape(-1, 3)] * 3          # dof 3 i + j sits on vertex j of cell i
+        idg.w_sub_copy = [np.zeros(3 * nF) for _ in range(3)]
+        idg.sub_dofmaps = [_SubDofmap()] * 3
+        idg.dof_coords = np.repeat(xyz[cells][:, None, :, :], 3, axis=1).reshape(-1, 3)   # dof 12 c + 4 k + v
+        idg.ws = [_Vec(got, k) for k in range(3)]
+        idg.fa = types.SimpleNamespace(assign=lambda *a: None)
+        idg.v_sub = "v_sub"
+        u_vec = (np.arange(12 * nc, dtype=np.int64) * 2654435761 % 1000003).astype(np.float64)   # distinct, exact
+        assert rc.InterpolateDG.__call__(idg, u_vec) == "v_sub"
+        out[f"idg_{name}_boundary"] = np.stack([got[k] for k in range(3)])       # (3 components, 3 nF)
+    # ---- loop: the reference's compute_hemodyanamics() itself, lines 160-372, on emulated dolfin objects
+    out.update(run_reference_time_loop(rc))
     # ---- args: the reference's argparse
     got = []
     for argv in ARGV_CASES:

@@ -102,3 +102,92 @@ def test_parse_arguments_matches_the_reference_parser():
         assert got == want, argv
         assert set(ns) - set(want) == {"velocity_degree", "device"}      # the two documented extensions
         assert ns["velocity_degree"] == 2 and ns["device"] is None       # ... default to the reference behaviour
+
+
+@pytest.mark.parametrize("name", ["cylinder", "stenosis"])
+def test_dof_copy_map_equals_the_reference_interpolate_dg(name):
+    """R5: the reference's own ``InterpolateDG.__call__`` (compute_hemodynamics.py:65-89: np.allclose coordinate
+    matching, first match wins) was run on duck-typed spaces over this mesh; copying with the oracle's
+    ``bcell_local`` -- the map the CUDA precompute reproduces bit-exactly -- must give the same boundary vectors."""
+    from oracle import hemo_oracle as ho
+    from tests import helpers as H
+    src = H.load_fluid(name)
+    S = ho.SurfaceStress(src["xyz"], src["tets"], 1.0, 1)
+    nc = len(S.tets)
+    u_vec = (np.arange(12 * nc, dtype=np.int64) * 2654435761 % 1000003).astype(np.float64)
+    x = u_vec.reshape(nc, 3, 4)                                     # dof 12 c + 4 k + v
+    m = S.maps
+    got = x[m.facet_cell[:, None], :, m.bcell_local.astype(np.int64)]       # (nF, 3 boundary dofs j, 3 components k)
+    want = G[f"idg_{name}_boundary"].reshape(3, S.nF, 3).transpose(1, 2, 0)  # stored (k, 3 i + j)
+    assert np.array_equal(got, want)
+    assert len(np.unique(u_vec)) == len(u_vec)                      # a wrong dof could not go unnoticed
+
+
+def _loop_case():
+    from oracle import hemo_oracle as ho
+    from tests import helpers as H
+    from vasp_b200 import synth
+    cfg = _j("loop_seed")
+    src = H.load_fluid(cfg["mesh"])
+    xyz, tets = src["xyz"], src["tets"]
+    rx, rt = synth.refine_uniform(xyz, tets, seed=cfg["refine_seed"])
+    vecs = synth.velocity_series(synth.velocity_basis(rx, seed=cfg["basis_seed"]), G["loop_coef"])
+    times = [cfg["dt"] * (k + 1) for k in range(cfg["n_snap"])]
+    node_of_p2 = ho.match_points(ho.p2_node_coordinates(xyz, ho.p2_cell_nodes(tets)[1]), rx, 1e-9)
+    return cfg, xyz, tets, rx, rt, vecs, times, ho.SurfaceStress(xyz, tets, cfg["mu"], 2, node_of_p2)
+
+
+def test_time_loop_bookkeeping_equals_the_reference_function():
+    """``compute_hemodyanamics`` of the reference (compute_hemodynamics.py:160-372) was executed on emulated dolfin
+    objects with ``Stress`` and ``project_dg`` standing on the oracle's restatements (see make_reference_goldens.py);
+    the oracle's own loop -- which snapshots, dt, tau_prev = 0, magnitudes, sums, / counter, RRT / OSI / ECAP -- must
+    land on the same numbers."""
+    from oracle import hemo_oracle as ho
+    cfg, xyz, tets, rx, rt, vecs, times, S = _loop_case()
+    sel = list(range(0, cfg["n_snap"], cfg["stride"]))
+    assert np.allclose(G["loop_wss_times"], [times[k] for k in sel], rtol=0, atol=1e-15)
+    assert G["loop_wss_append"].all()
+    n = len(rx)
+    dt = times[sel[1]] - times[sel[0]]                     # the reference: timestamps of dataset[1] - dataset[0]
+    res = ho.run_time_loop(S, vecs[sel], dt, (0, n, 2 * n), keep_wss=True)
+    fin = ho.finalize(res["wss_sum"], res["tawss_sum"], res["twssg_sum"], res["count"])
+    assert np.array_equal(res["wss"].reshape(len(sel), -1), G["loop_wss"])
+    for name in ("TAWSS", "OSI", "RRT", "ECAP", "TWSSG"):
+        want = G["loop_" + name].reshape(-1, 3)
+        err = np.linalg.norm(fin[name] - want) / np.linalg.norm(want)
+        assert err < 1e-14, (name, err)
+    out = str(G["loop_stdout"])
+    assert out.count("Calculating WSS at Timestep") == len(sel) and "--- TAWSS is saved in" in out
+
+
+def test_entry_point_writes_what_the_reference_function_wrote(tmp_path, monkeypatch):
+    """Same inputs through this repository's entry point (stand-in engine): every ``write_checkpoint`` the reference
+    issued -- name, time, order, values -- must be in the files."""
+    from tests.fake_engine import OracleHemoEngine
+    from vasp_b200 import engine as engine_mod
+    cfg, xyz, tets, rx, rt, vecs, times, S = _loop_case()
+    monkeypatch.setattr(ch, "HemoEngine", OracleHemoEngine)
+    monkeypatch.setattr(ch, "pinned_empty", lambda shape: np.zeros(shape))
+    monkeypatch.setattr(engine_mod, "pinned_empty", lambda shape: np.zeros(shape))
+    for n_ in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(n_, raising=False)
+    (tmp_path / "Mesh").mkdir()
+    (tmp_path / "Visualization_separate_domain").mkdir()
+    for nm in ("mesh.h5", "mesh_fluid.h5"):
+        io_dolfin.write_mesh(tmp_path / "Mesh" / nm, xyz, tets)
+    io_dolfin.write_mesh(tmp_path / "Mesh" / "mesh_refined_fluid.h5", rx, rt)
+    io_dolfin.write_velocity_series(tmp_path / "Visualization_separate_domain" / "u.h5", rt, len(rx), vecs, times)
+    ch.compute_hemodyanamics(tmp_path / "Visualization_separate_domain", tmp_path / "Mesh" / "mesh.h5", cfg["mu"],
+                             cfg["stride"])
+    hemo = tmp_path / "Hemodynamic_indices"
+    _, ts, idx = io_turtle.output_file_lists(hemo / "WSS.xdmf")
+    assert np.allclose(ts, G["loop_wss_times"], rtol=0, atol=1e-15) and idx == list(range(len(ts)))
+    from vasp_b200.h5lite import H5File
+    with H5File(hemo / "WSS.h5") as f:
+        for k in range(len(ts)):
+            assert np.array_equal(f[f"WSS/WSS_{k}/vector"].read().ravel(), G["loop_wss"][k]), k
+    for name in ("TAWSS", "OSI", "RRT", "ECAP", "TWSSG"):
+        with H5File(hemo / f"{name}.h5") as f:
+            got = f[f"{name}/{name}_0/vector"].read().ravel()
+        want = G["loop_" + name]
+        assert np.linalg.norm(got - want) <= 1e-14 * np.linalg.norm(want), name
