@@ -343,6 +343,115 @@ def run_reference_time_loop(rc) -> dict:
     return res
 
 
+TURTLE_CASES = [(1, None, None), (2, None, None), (3, 0.01, 0.04), (1, 0.015, 0.03), (4, None, 0.045), (2, 0.035, 0.05)]
+
+
+def write_raw_turtle_case(folder: Path):
+    """A small results folder as turtleFSI + vasp-refine-mesh + vasp-separate-mesh leave it (raw velocity AND
+    displacement series, restarted once), with exactly representable values; shared by the generator and the test."""
+    from vasp_b200 import synth
+    meshes = np.load(HERE / "fluid_meshes.npz")
+    xyz, tets = meshes["cylinder_xyz"], meshes["cylinder_tets"].astype(np.int64)
+    rx, rt = synth.refine_uniform(xyz, tets, seed=3)
+    n_ref, n_all, n_steps, split_at, dt_save = len(rx), len(rx) + 90, 10, 6, 0.05
+    fluid_ids = np.sort((np.arange(n_ref) * 1 + (np.arange(n_ref) * 90) // n_ref))        # strictly increasing, gaps
+    solid_only = np.setdiff1d(np.arange(n_all), fluid_ids)
+    coords = np.zeros((n_all, 3))
+    coords[fluid_ids] = rx
+    coords[solid_only] = 100.0 + np.arange(len(solid_only))[:, None]
+    solid_cells = np.stack([solid_only[:60], solid_only[10:70], fluid_ids[:60], solid_only[20:80]], axis=1)
+    topo = np.concatenate([fluid_ids[rt], solid_cells]).astype("<i8")
+    domains = np.concatenate([np.full(len(rt), 1), np.full(len(solid_cells), 2)]).astype("<u8")
+    for sub in ("Mesh", "Visualization"):
+        (folder / sub).mkdir(parents=True)
+    io_dolfin.write_mesh(folder / "Mesh" / "mesh_refined_fluid.h5", rx, rt)
+    with H5Writer(folder / "Mesh" / "mesh_refined.h5") as w:
+        w.create_dataset("/mesh/coordinates", coords.astype("<f8"))
+        w.create_dataset("/mesh/topology", topo, attrs={"celltype": "tetrahedron"})
+        w.create_dataset("/domains/topology", topo)
+        w.create_dataset("/domains/values", domains)
+    node, comp = np.arange(n_all)[:, None], np.arange(3)[None, :]
+    for quantity in ("velocity", "displacement"):
+        files = [H5Writer(folder / "Visualization" / f"{quantity}.h5"),
+                 H5Writer(folder / "Visualization" / f"{quantity}_run_1.h5")]
+        for k in range(n_steps):
+            raw = ((node * 7 + comp * 3 + k * 11 + (5 if quantity == "displacement" else 0)) % 1009).astype(np.float64) \
+                + 0.25 * comp
+            which, idx = (0, k) if k < split_at else (1, k - split_at)
+            files[which].create_dataset(f"/VisualisationVector/{idx}", raw)
+        for f in files:
+            f.close()
+        txt = turtle_xdmf(n_steps, split_at, n_all, len(topo)).replace("velocity", quantity)
+        (folder / "Visualization" / f"{quantity}.xdmf").write_text(txt)
+    times = [0.001 * 5 * (k + 1) for k in range(n_steps)]
+    return {"fluid_ids": fluid_ids, "n_all": n_all, "times": times, "save_time_step": 0.005, "n_ref": n_ref}
+
+
+def run_reference_create_hdf5() -> dict:
+    """``create_hdf5`` of the reference (create_hdf5.py:24-189) executed on a raw turtleFSI folder with emulated dolfin
+    objects (``Function.vector().set_local``, an ``HDF5File`` that records every ``write(u, "/velocity", time)``):
+    which steps are converted for a given (stride, start, end), from which h5 file and index, the fluid-node slice and
+    the component-blocked flattening are the reference's."""
+    import hashlib
+    cr = importlib.import_module("vasp.postprocessing.postprocessing_fenics.create_hdf5")
+    written = []
+
+    class Vec:
+        def set_local(self, v):
+            self.a = np.array(v)
+
+    class Fn:
+        def __init__(self, space):
+            self.v = Vec()
+
+        def vector(self):
+            return self.v
+
+    class H5:
+        def __init__(self, comm, path, mode=None, file_mode=None):
+            self.path, self.mode = Path(path), mode or file_mode
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            pass
+
+        def read(self, *a):
+            pass
+
+        def close(self):
+            pass
+
+        def write(self, obj, name, *t):
+            if isinstance(obj, Fn):
+                written.append((self.path.name, self.mode, name, float(t[0]), obj.v.a.copy()))
+
+    cr.Mesh = lambda comm: object()
+    cr.MPI = types.SimpleNamespace(comm_self=None)
+    cr.HDF5File = H5
+    cr.VectorFunctionSpace = lambda mesh, fam, deg: None
+    cr.Function = Fn
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        info = write_raw_turtle_case(td)
+        (td / "Visualization_separate_domain").mkdir()
+        for k, (stride, st, et) in enumerate(TURTLE_CASES):
+            written.clear()
+            with redirect_stdout(io.StringIO()):
+                cr.create_hdf5(td / "Visualization", td / "Mesh" / "mesh_refined.h5", info["save_time_step"], stride,
+                               st, et, False, 1, 2)
+            u = [w for w in written if w[0] == "u.h5"]
+            assert u and all(w[2] == "/velocity" for w in u) and u[0][1] == "w" and all(w[1] == "a" for w in u[1:])
+            out[f"hdf5_{k}_times"] = np.array([w[3] for w in u])
+            out[f"hdf5_{k}_sha"] = np.array([hashlib.sha256(np.ascontiguousarray(w[4]).tobytes()).hexdigest() for w in u])
+            if k == 0:
+                out["hdf5_0_first_vector"] = u[0][4]
+    out["hdf5_cases"] = np.array(json.dumps(TURTLE_CASES))
+    return out
+
+
 def main() -> None:
     install_shims()
     pc = importlib.import_module("vasp.postprocessing.postprocessing_common")
@@ -456,6 +565,8 @@ def main() -> None:
         out[f"idg_{name}_boundary"] = np.stack([got[k] for k in range(3)])       # (3 components, 3 nF)
     # ---- loop: the reference's compute_hemodyanamics() itself, lines 160-372, on emulated dolfin objects
     out.update(run_reference_time_loop(rc))
+    # ---- hdf5: the reference's create_hdf5() on a raw turtleFSI folder
+    out.update(run_reference_create_hdf5())
     # ---- args: the reference's argparse
     got = []
     for argv in ARGV_CASES:

@@ -191,3 +191,32 @@ def test_entry_point_writes_what_the_reference_function_wrote(tmp_path, monkeypa
             got = f[f"{name}/{name}_0/vector"].read().ravel()
         want = G["loop_" + name]
         assert np.linalg.norm(got - want) <= 1e-14 * np.linalg.norm(want), name
+
+
+def test_raw_turtlefsi_series_equals_what_create_hdf5_wrote(tmp_path):
+    """SURVEY §8f-1.  ``create_hdf5`` of the reference (create_hdf5.py:24-189) was executed on this raw folder with an
+    ``HDF5File`` that records every ``write(u, "/velocity", time)``; the in-place reader must present the same steps,
+    times and -- after the fluid-node gather K1 performs -- the same vectors, for every (stride, start, end)."""
+    import hashlib
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_reference_goldens",
+                                                  Path(__file__).resolve().parent / "golden" / "make_reference_goldens.py")
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)                         # only its folder writer is used; no shim is installed
+    info = gen.write_raw_turtle_case(tmp_path)
+    cases = _j("hdf5_cases")
+    assert len(cases) == 6
+    for k, (stride, st, et) in enumerate(cases):
+        s = io_turtle.TurtleVelocitySeries(tmp_path / "Visualization", tmp_path / "Mesh" / "mesh_refined.h5",
+                                           info["save_time_step"], stride, st, et, 1, 2, compute_stride=1)
+        want_t = G[f"hdf5_{k}_times"]
+        assert len(s) == len(want_t) and np.array_equal(s.timestamps, want_t), (k, s.timestamps, want_t)
+        off, node_stride, perm = s.layout(None, info["n_ref"])
+        buf = np.zeros((len(s), s.vec_len))
+        s.read_into(buf, 0, len(s))
+        for i in range(len(s)):
+            flat = np.concatenate([buf[i][off[c] + node_stride * perm] for c in range(3)])   # what K1 gathers
+            assert hashlib.sha256(flat.tobytes()).hexdigest() == str(G[f"hdf5_{k}_sha"][i]), (k, i)
+            if k == 0 and i == 0:
+                assert np.array_equal(flat, G["hdf5_0_first_vector"])
+        s.close()
