@@ -452,6 +452,82 @@ def run_reference_create_hdf5() -> dict:
     return out
 
 
+MAIN_SCENARIOS = [
+    # (name, files to create under the folder, parameters or None / "broken", argv after --folder F)
+    ("separate_domain_present", ["Visualization_separate_domain/", "Mesh/mesh.h5"],
+     {"save_deg": 2, "dt": 0.001, "save_step": 5, "mu_f": 0.0035, "dx_f_id": 1, "dx_s_id": 2}, []),
+    ("two_viscosities_stride_user_mesh", ["Visualization_separate_domain/", "elsewhere/my_mesh.h5"],
+     {"save_deg": 2, "dt": 0.001, "save_step": 5, "mu_f": [0.0035, 0.005], "dx_f_id": 1, "dx_s_id": 2},
+     ["--stride", "3", "--mesh-path", "<F>/elsewhere/my_mesh.h5"]),
+    ("raw_output_refined_mesh", ["Mesh/mesh.h5", "Mesh/mesh_refined.h5"],
+     {"save_deg": 2, "dt": 0.001, "save_step": 5, "mu_f": 0.0035, "dx_f_id": 1, "dx_s_id": [2, 1002]}, ["--stride", "2"]),
+    ("raw_output_window_entire_domain", ["Mesh/mesh.h5", "Mesh/mesh_refined.h5", "elsewhere/m.h5"],
+     {"save_deg": 2, "dt": 0.002, "save_step": 10, "mu_f": 0.0035, "dx_f_id": [1, 1001], "dx_s_id": 2},
+     ["-st", "0.1", "-et", "0.5", "--extract-entire-domain", "--mesh-path", "<F>/elsewhere/m.h5"]),
+    ("folder_missing", None, None, []),
+    ("parameters_missing", ["Visualization_separate_domain/", "Mesh/mesh.h5"], None, []),
+    ("parameters_broken", ["Visualization_separate_domain/", "Mesh/mesh.h5"], "broken", []),
+    ("save_deg_1", ["Visualization_separate_domain/", "Mesh/mesh.h5"],
+     {"save_deg": 1, "dt": 0.001, "save_step": 5, "mu_f": 0.0035, "dx_f_id": 1, "dx_s_id": 2}, []),
+    ("raw_output_refined_mesh_missing", ["Mesh/mesh.h5"],
+     {"save_deg": 2, "dt": 0.001, "save_step": 5, "mu_f": 0.0035, "dx_f_id": 1, "dx_s_id": 2}, []),
+    ("default_mesh_missing", ["Visualization_separate_domain/"],
+     {"save_deg": 2, "dt": 0.001, "save_step": 5, "mu_f": 0.0035, "dx_f_id": 1, "dx_s_id": 2}, []),
+    ("user_mesh_missing", ["Visualization_separate_domain/", "Mesh/mesh.h5"],
+     {"save_deg": 2, "dt": 0.001, "save_step": 5, "mu_f": 0.0035, "dx_f_id": 1, "dx_s_id": 2},
+     ["--mesh-path", "<F>/nowhere.h5"]),
+]
+
+
+def make_scenario(base: Path, files, params) -> Path:
+    """Folder of one MAIN_SCENARIOS entry (shared by the generator and the test)."""
+    f = base / "case"
+    if files is None:
+        return f
+    f.mkdir(parents=True)
+    for rel in files:
+        p = f / rel
+        if rel.endswith("/"):
+            p.mkdir(parents=True, exist_ok=True)
+        else:
+            p.parent.mkdir(parents=True, exist_ok=True)
+            p.write_bytes(b"")
+    if params is not None:
+        (f / "Checkpoint").mkdir()
+        (f / "Checkpoint" / "default_variables.json").write_text("{ not json" if params == "broken" else json.dumps(params))
+    return f
+
+
+def run_reference_main(rc) -> dict:
+    """``main()`` of the reference (compute_hemodynamics.py:375-455) with ``create_hdf5`` and ``compute_hemodyanamics``
+    replaced by recorders: which checks fire, which messages are printed, what the two stages are called with."""
+    results = {}
+    rc.MPI = types.SimpleNamespace(comm_world=types.SimpleNamespace(barrier=lambda: None), size=lambda c: 1,
+                                   rank=lambda c: 0)
+    for name, files, params, argv in MAIN_SCENARIOS:
+        calls = []
+        rc.create_hdf5 = lambda *a: calls.append(["create_hdf5"] + list(a))
+        rc.compute_hemodyanamics = lambda *a: calls.append(["compute_hemodyanamics"] + list(a))
+        with tempfile.TemporaryDirectory() as td:
+            F = make_scenario(Path(td), files, params)
+            old = sys.argv
+            sys.argv = ["vasp-compute-hemo", "--folder", str(F)] + [a.replace("<F>", str(F)) for a in argv]
+            log, err = io.StringIO(), None
+            try:
+                with redirect_stdout(log):
+                    rc.main()
+            except (AssertionError, RuntimeError) as e:
+                err = [type(e).__name__, str(e).replace(str(F), "<F>")]
+            finally:
+                sys.argv = old
+
+            def plain(v):
+                return str(v).replace(str(F), "<F>") if isinstance(v, Path) else v
+            results[name] = {"stdout": [ln for ln in log.getvalue().replace(str(F), "<F>").splitlines() if ln.strip()],
+                             "error": err, "calls": [[plain(v) for v in c] for c in calls]}
+    return {"main": np.array(json.dumps(results))}
+
+
 def main() -> None:
     install_shims()
     pc = importlib.import_module("vasp.postprocessing.postprocessing_common")
@@ -565,6 +641,8 @@ def main() -> None:
         out[f"idg_{name}_boundary"] = np.stack([got[k] for k in range(3)])       # (3 components, 3 nF)
     # ---- loop: the reference's compute_hemodyanamics() itself, lines 160-372, on emulated dolfin objects
     out.update(run_reference_time_loop(rc))
+    # ---- main: the reference's main() with both stages recorded
+    out.update(run_reference_main(rc))
     # ---- hdf5: the reference's create_hdf5() on a raw turtleFSI folder
     out.update(run_reference_create_hdf5())
     # ---- args: the reference's argparse

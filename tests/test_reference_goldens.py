@@ -220,3 +220,61 @@ def test_raw_turtlefsi_series_equals_what_create_hdf5_wrote(tmp_path):
             if k == 0 and i == 0:
                 assert np.array_equal(flat, G["hdf5_0_first_vector"])
         s.close()
+
+
+def _generator_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_reference_goldens",
+                                                  Path(__file__).resolve().parent / "golden" / "make_reference_goldens.py")
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    return gen
+
+
+def test_main_behaves_like_the_reference_main(tmp_path, monkeypatch, capsys):
+    """``main()`` of the reference (compute_hemodynamics.py:375-455) was run over eleven folder layouts / command lines
+    with its two stages replaced by recorders.  Same scenarios here: same exception type and message, same printed
+    lines in the same order (the one line announcing the u.h5 conversion is replaced by the in-place reader's), the
+    raw series opened with the arguments ``create_hdf5`` got, ``compute_hemodyanamics`` called with the same four."""
+    gen = _generator_module()
+    want_all = _j("main")
+    for n_ in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(n_, raising=False)
+    for i, (name, files, params, argv) in enumerate(gen.MAIN_SCENARIOS):
+        want = want_all[name]
+        F = gen.make_scenario(tmp_path / f"s{i}", files, params)
+        calls = []
+
+        class Series:
+            def __init__(self, *a, **k):
+                assert not k
+                calls.append(["series"] + list(a))
+
+        def compute(*a, **k):
+            calls.append(["compute_hemodyanamics"] + list(a) + [k.get("series")])
+
+        monkeypatch.setattr(io_turtle, "TurtleVelocitySeries", Series)
+        monkeypatch.setattr(ch, "compute_hemodyanamics", compute)
+        err = None
+        try:
+            ch.main(["--folder", str(F)] + [a.replace("<F>", str(F)) for a in argv])
+        except (AssertionError, RuntimeError) as e:
+            err = [type(e).__name__, str(e).replace(str(F), "<F>")]
+        assert err == want["error"], name
+        out = [ln for ln in capsys.readouterr().out.replace(str(F), "<F>").splitlines() if ln.strip()]
+        ref_lines = [ln for ln in want["stdout"] if "Creating HDF5 file" not in ln]
+        it = iter(out)
+        assert all(any(ln.strip() == mine.strip() for mine in it) for ln in ref_lines), (name, out, ref_lines)
+
+        def plain(v):
+            return str(v).replace(str(F), "<F>") if isinstance(v, Path) else v
+        mine = [[plain(v) for v in c] for c in calls]
+        ref_calls = want["calls"]
+        if ref_calls and ref_calls[0][0] == "create_hdf5":
+            c = ref_calls[0]      # (visualization_path, mesh_path, save_time_step, stride, start, end, solid_only, fid, sid)
+            assert mine[0] == ["series", c[1], c[2], c[3], c[4], c[5], c[6], c[8], c[9]], name
+            assert isinstance(calls[1][-1], Series), name                 # ... and that series is what gets computed on
+            mine, ref_calls = mine[1:], ref_calls[1:]
+        assert len(mine) == len(ref_calls), name
+        for a, b in zip(mine, ref_calls):
+            assert a[:5] == b, name                                       # (folder, mesh_path, mu_f, stride)
