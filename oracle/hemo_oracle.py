@@ -10,7 +10,8 @@ single test are not shipped (``.MISSING_LARGE_BLOBS``).  What *is* pinned: the r
 (``tests/test_compute_hemodynamics.py:68-73``: wall-averaged TAWSS of Poiseuille flow in (1.95, 2.05)) and its
 OSI range assertion (``:84-88``, ``compute_hemodynamics.py:366-372``); see ``tests/test_oracle.py``.  Also pinned, by
 RUNNING the reference's own Python in the build container (``tests/golden/make_reference_goldens.py`` ->
-``tests/test_reference_goldens.py``): the dof copy map against ``InterpolateDG.__call__`` (``:65-89``) and the whole
+``tests/test_reference_goldens.py``): the traction formula against the UFL expression of ``Stress.__init__``
+(``:142-150``) evaluated with numeric operands, the dof copy map against ``InterpolateDG.__call__`` (``:65-89``) and the whole
 time-loop bookkeeping against ``compute_hemodyanamics`` (``:160-372``) executed on emulated dolfin objects, with only
 ``Stress`` and ``project_dg`` standing on this file's restatements.  Still unpinned: the finite-element assembly
 inside dolfin/FFC (facet quadrature, the 7-point rule of ``project_dg``) and dolfin's boundary-mesh numbering.

@@ -452,6 +452,59 @@ def run_reference_create_hdf5() -> dict:
     return out
 
 
+def run_reference_stress_expression(rc) -> dict:
+    """``Stress.__init__`` of the reference (compute_hemodynamics.py:142-150) evaluated numerically: ``grad``, ``sym``,
+    ``FacetNormal`` and ``inner`` are bound to tiny numpy-backed tensor / vector / scalar classes that implement the
+    operators the UFL expression uses (scalar * tensor, tensor * vector, unary minus, vector - vector, scalar * vector),
+    so ``self.Ft`` comes out as a number for a given velocity gradient G and facet normal n: sign conventions, the
+    factor 2 mu, sym() and the tangential projection are the reference's lines, not a restatement."""
+    class Sc:
+        def __init__(self, a):
+            self.a = float(a)
+
+        def __mul__(self, o):
+            return Vc(self.a * o.a)
+
+    class Vc:
+        def __init__(self, a):
+            self.a = np.asarray(a, dtype=np.float64)
+
+        def __neg__(self):
+            return Vc(-self.a)
+
+        def __sub__(self, o):
+            return Vc(self.a - o.a)
+
+    class Tn:
+        def __init__(self, a):
+            self.a = np.asarray(a, dtype=np.float64)
+
+        def __rmul__(self, s_):
+            return Tn(s_ * self.a)
+
+        def __mul__(self, v):
+            return Vc(self.a @ v.a)
+
+    state = {}
+    rc.SurfaceProjector = lambda V: None
+    rc.InterpolateDG = lambda *a: None
+    rc.grad = lambda u: Tn(state["G"])
+    rc.sym = lambda t: Tn(0.5 * (t.a + t.a.T))
+    rc.FacetNormal = lambda mesh: Vc(state["n"])
+    rc.inner = lambda a, b: Sc(a.a @ b.a)
+    V = types.SimpleNamespace(ufl_element=lambda: types.SimpleNamespace(family=lambda: "Discontinuous Lagrange"))
+    rng = np.random.default_rng(11)
+    Gs, ns, mus, fts = [], [], [], []
+    for _ in range(12):
+        state["G"] = rng.normal(size=(3, 3))
+        nrm = rng.normal(size=3)
+        state["n"] = nrm / np.linalg.norm(nrm)
+        mu_ = float(rng.uniform(1e-3, 2.0))
+        st = rc.Stress(u=None, V_dg=V, V_sub=V, mu_f=mu_, mesh=None, boundary_mesh=None)
+        Gs.append(state["G"]), ns.append(state["n"]), mus.append(mu_), fts.append(st.Ft.a)
+    return {"stress_G": np.array(Gs), "stress_n": np.array(ns), "stress_mu": np.array(mus), "stress_Ft": np.array(fts)}
+
+
 MAIN_SCENARIOS = [
     # (name, files to create under the folder, parameters or None / "broken", argv after --folder F)
     ("separate_domain_present", ["Visualization_separate_domain/", "Mesh/mesh.h5"],
@@ -639,6 +692,8 @@ def main() -> None:
         u_vec = (np.arange(12 * nc, dtype=np.int64) * 2654435761 % 1000003).astype(np.float64)   # distinct, exact
         assert rc.InterpolateDG.__call__(idg, u_vec) == "v_sub"
         out[f"idg_{name}_boundary"] = np.stack([got[k] for k in range(3)])       # (3 components, 3 nF)
+    # ---- stress: the UFL expression of Stress.__init__ evaluated with numeric operands (before rc.Stress is replaced)
+    out.update(run_reference_stress_expression(rc))
     # ---- loop: the reference's compute_hemodyanamics() itself, lines 160-372, on emulated dolfin objects
     out.update(run_reference_time_loop(rc))
     # ---- main: the reference's main() with both stages recorded

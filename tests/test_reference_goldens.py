@@ -278,3 +278,25 @@ def test_main_behaves_like_the_reference_main(tmp_path, monkeypatch, capsys):
         assert len(mine) == len(ref_calls), name
         for a, b in zip(mine, ref_calls):
             assert a[:5] == b, name                                       # (folder, mesh_path, mu_f, stride)
+
+
+def test_traction_formula_equals_the_reference_expression():
+    """R3: ``Stress.__init__`` (compute_hemodynamics.py:142-150) was evaluated with numeric tensor / vector operands
+    (see make_reference_goldens.py).  The oracle's ``_traction_at`` gets a linear field u(x) = G x on a tetrahedron
+    (so grad u = G exactly) and the same normal, and must return the same Ft."""
+    from oracle import hemo_oracle as ho
+    xyz = np.array([[0.1, 0.2, 0.0], [1.3, 0.1, 0.2], [0.2, 1.1, 0.1], [0.3, 0.2, 0.9]])
+    tets = np.array([[0, 1, 2, 3]])
+    worst = 0.0
+    for G_, n_, mu_, ft in zip(G["stress_G"], G["stress_n"], G["stress_mu"], G["stress_Ft"]):
+        for order in (1, 2):
+            S = ho.SurfaceStress(xyz, tets, float(mu_), order)
+            pts = xyz if order == 1 else ho.p2_node_coordinates(xyz, S.edges)
+            u_nodes = pts @ G_.T                                       # u_i = G_ij x_j at every velocity node
+            u_cell = np.broadcast_to(u_nodes[S.maps.cell_nodes[0]], (S.nF,) + u_nodes[S.maps.cell_nodes[0]].shape)
+            S.normal = np.broadcast_to(n_, (S.nF, 3)).copy()           # the formula is under test, not the geometry
+            lam = np.zeros((S.nF, 1, 4))
+            lam[:, 0, :] = [0.2, 0.3, 0.1, 0.4]
+            got = S._traction_at(u_cell, lam)[:, 0, :]
+            worst = max(worst, np.abs(got - ft).max() / np.abs(ft).max())
+    assert worst < 1e-13, worst
