@@ -4,7 +4,6 @@ row of the block is an identity row any more).  The four reference meshes only c
 import numpy as np
 import pytest
 
-from oracle import hemo_oracle as ho
 from tests import helpers as H
 
 pytestmark = pytest.mark.gpu

@@ -4,7 +4,6 @@ the vertex / cell numbering.  None of them needs a second implementation to comp
 import numpy as np
 import pytest
 
-from oracle import hemo_oracle as ho
 from tests import helpers as H
 
 MU = 0.8
