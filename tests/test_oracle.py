@@ -176,3 +176,40 @@ def test_c_twin_matches_numpy_restatement(order):
     r1 = co.run(case["u"][:5], case["dt"], (0, n, 2 * n))
     r2 = co.run(case["u"][5:], case["dt"], (0, n, 2 * n), tau_prev=r1["tau_last"])
     assert H.rel_l2(r1["twssg_sum"] + r2["twssg_sum"], res["twssg_sum"]) < 1e-13
+
+
+def test_quadrature_rules_are_what_they_claim():
+    """The two facet rules of the restatement.  A 7-point rule on the triangle that is exact to degree 5 and has the
+    centroid + two 3-point orbits structure is unique (Radon's rule, the one FIAT's default scheme tabulates for degree 5
+    -- which rule FIAT picks is [dolfin-recall], that these numbers *are* that rule is checked here in exact arithmetic):
+    the closed forms are  a, b = (6 -/+ sqrt(15)) / 21,  weights (155 -/+ sqrt(15)) / 1200, centroid 9 / 40."""
+    import math
+    import sympy as sp
+    r15 = sp.sqrt(15)
+    a1, a2 = (6 - r15) / 21, (6 + r15) / 21
+    w1, w2 = (155 - r15) / 1200, (155 + r15) / 1200
+    pts = [(sp.Rational(1, 3),) * 3]
+    for a, in ((a1,), (a2,)):
+        b = 1 - 2 * a
+        pts += [(a, b, a), (a, a, b), (b, a, a)]
+    wts = [sp.Rational(9, 40)] + [w1] * 3 + [w2] * 3
+    got_pts = np.array([[float(c) for c in p] for p in pts])
+    assert np.allclose(np.sort(got_pts, axis=None), np.sort(ho.Q5_PTS, axis=None), rtol=0, atol=1e-15)
+    assert np.allclose(sorted(float(w) for w in wts), sorted(ho.Q5_WTS), rtol=0, atol=1e-15)
+    # exactness on the reference triangle: integral of l0^i l1^j l2^k / area = 2 i! j! k! / (i + j + k + 2)!
+    for deg in range(6):
+        for i in range(deg + 1):
+            for j in range(deg + 1 - i):
+                k = deg - i - j
+                exact = sp.Rational(2 * math.factorial(i) * math.factorial(j) * math.factorial(k),
+                                    math.factorial(deg + 2))
+                num = sp.simplify(sum(w * p[0] ** i * p[1] ** j * p[2] ** k for w, p in zip(wts, pts)))
+                assert num == exact, (i, j, k)
+    # ... and not to degree 6 (it is a degree-5 rule, not something better)
+    num6 = sp.simplify(sum(w * p[0] ** 6 for w, p in zip(wts, pts)))
+    assert num6 != sp.Rational(2 * math.factorial(6), math.factorial(8))
+    # the 3-point rule of the traction integral is exact to degree 2
+    q2p, q2w = ho._Q2_PTS, ho._Q2_WTS
+    for i, j, k in ((0, 0, 0), (1, 0, 0), (0, 1, 0), (2, 0, 0), (1, 1, 0), (0, 1, 1), (0, 0, 2)):
+        exact = 2 * math.factorial(i) * math.factorial(j) * math.factorial(k) / math.factorial(i + j + k + 2)
+        assert abs(np.sum(q2w * q2p[:, 0] ** i * q2p[:, 1] ** j * q2p[:, 2] ** k) - exact) < 1e-15
