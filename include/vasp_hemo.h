@@ -74,7 +74,8 @@ int vh_get_sizes(vh_handle* h, int64_t n[7]);
 
 /* Index maps for bit-exact checks against the oracle and for the output writer (any pointer may be NULL):
  *   facet_cell[nF], facet_local[nF] (face opposite local vertex k), facet_verts[nF*3] ascending parent vertex ids,
- *   bcell_parent[nF*3] parent vertex ids in boundary-cell order (dolfin BoundaryComputation orientation),
+ *   bcell_parent[nF*3] parent vertex ids in boundary-cell order (BoundaryMesh(..., order=True): ascending in
+ *   boundary vertex number),
  *   btopology[nF*3] boundary-vertex numbers, bvert_parent[nBV], bcell_local[nF*3] local cell vertex of each
  *   boundary dof (InterpolateDG's copy map :65-89), facet_nodes[nF*ndof] velocity node of each cell dof. */
 int vh_get_maps(vh_handle* h, int32_t* facet_cell, int8_t* facet_local, int32_t* facet_verts,
@@ -113,6 +114,36 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
 /* Same, for vectors already resident in device memory (wss_out is a device pointer or NULL). */
 int vh_push_snapshots_device(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_bytes, int flags,
                              double* d_wss_out);
+
+/* ---- wall-layer compaction in front of the bus ----------------------------------------------------------------
+ * The reference integrates over ds only (compute_hemodynamics.py:113-115): of a snapshot vector (:274) only the dofs
+ * of cells that own an exterior facet reach the result (n[6] of vh_get_sizes: 72 % of the nodes on the tutorial-size
+ * mesh, 7 % at 10 M tets).  A COMPACT BLOCK of a snapshot is C[c * nWp + i] = vec[comp_offset[c] + slot[i]], c < 3,
+ * i < nWp = n[6] rounded up to a multiple of 32 (the padding repeats the last node); compact_len = 3 * nWp doubles.
+ * vh_push_snapshots gathers it on the host (a thread pool inside the library, pinned ring, overlapped with the copies)
+ * when that pays: mode 0 = automatic (wall-layer share of the vector below ~1/3), 1 = never, 2 = always.
+ * threads = gather threads (0 = hardware threads / ranks on the node, at most 32). */
+int vh_set_host_compaction(vh_handle* h, int mode, int threads);
+int vh_get_compact_info(vh_handle* h, int64_t* compact_len, int* active);
+/* slot[i], i < n[6]: element offset of wall-layer node i inside a snapshot vector (ascending). */
+int vh_get_wall_slots(vh_handle* h, int64_t* slots);
+/* Host gather only (no device work): out[r * compact_len ...] = compact block of snapshot r.  The rows may live in
+ * any host memory, e.g. an mmap of u.h5 -- the page cache is then gathered in place instead of being copied whole
+ * (replaces HDF5File.read(u, name), compute_hemodynamics.py:274, for the dofs that matter). */
+int vh_compact_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t stride_bytes, double* out);
+int vh_compact_rows(vh_handle* h, const double* const* rows, int64_t n_snap, double* out);
+/* The same gather without a handle (no GPU needed): out[r][c * n_slots + i] = row_r[comp_offset[c] + slots[i]]; rows
+ * are given either by address (rows != NULL) or as base + r * stride_bytes. */
+int vh_host_gather(const double* const* rows, const double* base, int64_t stride_bytes, int64_t n,
+                   const int32_t* slots, int64_t n_slots, const int64_t comp_offset[3], double* out,
+                   int64_t out_stride_bytes, int threads);
+/* Same contract as vh_push_snapshots / vh_push_snapshots_device for snapshots that already are compact blocks
+ * (consecutive ones stride_bytes >= 8 * compact_len apart); K1 is then a pure transpose. */
+int vh_push_compact(vh_handle* h, const double* c, int64_t n_snap, int64_t stride_bytes, int flags, double* wss_out);
+int vh_push_compact_device(vh_handle* h, const double* d_c, int64_t n_snap, int64_t stride_bytes, int flags,
+                           double* d_wss_out);
+/* Host milliseconds spent gathering and bytes copied host -> device since vh_begin. */
+int vh_get_io_stats(vh_handle* h, double* gather_ms, int64_t* h2d_bytes);
 
 /* ---- reductions / results ------------------------------------------------------------------------------- */
 /* Running sums as 15 rows of nF doubles (SoA): rows 0-8 sum tau (row 3*j+c: boundary dof j, component c),

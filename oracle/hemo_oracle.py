@@ -27,7 +27,7 @@ function here          reference lines
 =====================  =========================================================================
 ``order_cells``        dolfin ``Mesh.order()`` on read (``:187-189``) [dolfin-recall]
 ``exterior_facets``    ``BoundaryMesh(mesh, "exterior")`` ``:191`` + facet->cell ``:59-61``
-``boundary_mesh``      dolfin ``BoundaryComputation`` vertex numbering/orientation [dolfin-recall]
+``boundary_mesh``      dolfin ``BoundaryComputation`` vertex numbering + ``Mesh.order()`` (``order=True``) [dolfin-recall]
 ``p2_cell_nodes``      ``VectorFunctionSpace(mesh, "CG", 2)`` ``:206`` (UFC P2 local order)
 ``match_points``       ``PETScDMCollection.create_transfer_matrix`` ``:223`` applied at ``:275``
 ``SurfaceStress``      ``Stress`` ``:120-157``, ``SurfaceProjector`` ``:92-117``, ``InterpolateDG`` ``:32-89``
@@ -81,7 +81,11 @@ def exterior_facets(tets: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarra
     nc = tets.shape[0]
     keep = np.array([[1, 2, 3], [0, 2, 3], [0, 1, 3], [0, 1, 2]])
     faces = tets[:, keep].reshape(-1, 3)  # row 4*cell + k, already ascending
-    order = np.lexsort((faces[:, 2], faces[:, 1], faces[:, 0]))
+    nv = int(tets.max()) + 1
+    if nv < (1 << 21):  # the triple fits one int64 key: same lexicographic order, one sort instead of three
+        order = np.argsort((faces[:, 0] * nv + faces[:, 1]) * nv + faces[:, 2], kind="stable")
+    else:
+        order = np.lexsort((faces[:, 2], faces[:, 1], faces[:, 0]))
     fs = faces[order]
     same_next = np.zeros(len(fs), dtype=bool)
     same_next[:-1] = (fs[1:] == fs[:-1]).all(axis=1)
@@ -94,27 +98,24 @@ def exterior_facets(tets: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarra
 
 def boundary_mesh(xyz: np.ndarray, tets: np.ndarray, facets: np.ndarray, facet_cell: np.ndarray,
                   facet_local: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """Boundary triangle mesh the way dolfin's ``BoundaryComputation`` builds it.
+    """Boundary triangle mesh the way ``BoundaryMesh(mesh, "exterior")`` (``compute_hemodynamics.py:191``) builds it.
 
     Returns ``(bvert_parent (nBV,), btopology (nF,3) boundary vertex numbers, bcell_parent (nF,3) parent vertex
-    ids in boundary-cell vertex order)``.  Boundary vertices are numbered by first encounter over exterior
-    facets in facet order; the first two vertices of a boundary cell are swapped when (p1-p0)x(p2-p0) would
-    point towards the opposite cell vertex.
+    ids in boundary-cell vertex order)``.  dolfin's ``BoundaryComputation`` numbers the boundary vertices by first
+    encounter over the exterior facets in facet order; the reference leaves ``order`` at its default ``True``, so
+    ``Mesh.order()`` runs afterwards and every boundary cell lists its vertices ascending in *boundary* vertex
+    number (the right-oriented variant, first two vertices swapped towards the outward normal, is what
+    ``order=False`` would give and is not what the reference uses).
     """
-    tets = order_cells(tets)
     flat = facets.reshape(-1)
     _, first = np.unique(flat, return_index=True)
     first.sort()
     bvert_parent = flat[first]
     number = np.full(int(xyz.shape[0]), -1, dtype=np.int64)
     number[bvert_parent] = np.arange(len(bvert_parent))
-    opp = tets[facet_cell, facet_local.astype(np.int64)]
-    p0, p1, p2, p = xyz[facets[:, 0]], xyz[facets[:, 1]], xyz[facets[:, 2]], xyz[opp]
-    n = np.cross(p1 - p0, p2 - p0)
-    swap = np.einsum("ij,ij->i", n, p0 - p) < 0.0
-    bcell_parent = facets.copy()
-    bcell_parent[swap, 0], bcell_parent[swap, 1] = facets[swap, 1], facets[swap, 0]
-    return bvert_parent, number[bcell_parent], bcell_parent
+    bnum = number[facets]
+    perm = np.argsort(bnum, axis=1, kind="stable")
+    return bvert_parent, np.take_along_axis(bnum, perm, axis=1), np.take_along_axis(facets, perm, axis=1)
 
 
 def mesh_edges(tets: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:

@@ -39,6 +39,31 @@ def test_no_gpu_means_loud_failure_not_a_fallback():
         HemoEngine(0)
 
 
+def test_host_gather_of_the_wall_layer_is_a_pure_copy():
+    """csrc/compact.cu: the host-side compaction in front of the bus (handle-free entry point, no GPU needed) picks
+    vec[comp_offset[c] + slot[i]] bit for bit -- blocked and interleaved layouts, rows by stride and by address."""
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    n_nodes, n_w, n = 70001, 20011, 7
+    slots = np.sort(rng.choice(n_nodes, n_w, replace=False)).astype(np.int32)
+    for off, node_stride in (((0, n_nodes, 2 * n_nodes), 1), ((0, 1, 2), 3)):
+        u = rng.normal(size=(n, 3 * n_nodes + 5))
+        sl = (slots * node_stride).astype(np.int32)
+        want = np.stack([np.concatenate([u[r, o + sl.astype(np.int64)] for o in off]) for r in range(n)])
+        offs = (ctypes.c_int64 * 3)(*off)
+        for threads in (1, 3):
+            got = np.full((n, 3 * n_w + 2), -7.0)
+            rc = lib.vh_host_gather(None, u.ctypes.data, u.strides[0], n, sl.ctypes.data, n_w, offs, got.ctypes.data,
+                                    got.strides[0], threads)
+            assert rc == 0 and np.array_equal(got[:, :3 * n_w], want) and np.all(got[:, 3 * n_w:] == -7.0)
+        rows = np.array([u[r].ctypes.data for r in (4, 0, 6)], dtype=np.uint64)
+        got = np.empty((3, 3 * n_w))
+        assert lib.vh_host_gather(rows.ctypes.data, None, 0, 3, sl.ctypes.data, n_w, offs, got.ctypes.data,
+                                  got.strides[0], 2) == 0
+        assert np.array_equal(got, want[[4, 0, 6]])
+    assert lib.vh_host_gather(None, None, 0, 1, slots.ctypes.data, n_w, offs, got.ctypes.data, got.strides[0], 1) != 0
+
+
 def test_product_never_imports_the_oracle():
     for p in (ROOT / "vasp_b200").rglob("*.py"):
         src = p.read_text()

@@ -39,6 +39,15 @@ _SIGNATURES = {
     "vh_set_wss_layout": [_P, _I64, _I64],
     "vh_push_snapshots": [_P, _P, _I64, _I64, C.c_int, _P],
     "vh_push_snapshots_device": [_P, _P, _I64, _I64, C.c_int, _P],
+    "vh_set_host_compaction": [_P, C.c_int, C.c_int],
+    "vh_get_compact_info": [_P, C.POINTER(_I64), C.POINTER(C.c_int)],
+    "vh_get_wall_slots": [_P, _P],
+    "vh_compact_snapshots": [_P, _P, _I64, _I64, _P],
+    "vh_compact_rows": [_P, _P, _I64, _P],
+    "vh_host_gather": [_P, _P, _I64, _I64, _P, _I64, C.POINTER(_I64), _P, _I64, C.c_int],
+    "vh_push_compact": [_P, _P, _I64, _I64, C.c_int, _P],
+    "vh_push_compact_device": [_P, _P, _I64, _I64, C.c_int, _P],
+    "vh_get_io_stats": [_P, C.POINTER(_DBL), C.POINTER(_I64)],
     "vh_get_sums": [_P, _P, C.POINTER(_I64)],
     "vh_set_sums": [_P, _P, _I64],
     "vh_sums_device_ptr": [_P, C.POINTER(_P)],

@@ -13,7 +13,7 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
-SOURCES = ["abi.cu", "k0_precompute.cu", "k1_stage.cu", "k2_wall.cu"]
+SOURCES = ["abi.cu", "compact.cu", "k0_precompute.cu", "k1_stage.cu", "k2_wall.cu"]
 OUT = HERE / "libvasp_hemo.so"
 
 NVCC_FLAGS = [
@@ -36,7 +36,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; libvasp_hemo.so cannot be built")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(OUT), *[str(CSRC / s) for s in SOURCES], "-ldl"]
+    cmd = [nvcc, *NVCC_FLAGS, "-o", str(OUT), *[str(CSRC / s) for s in SOURCES], "-ldl", "-lpthread"]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
         print(" ".join(cmd), flush=True)

@@ -3,6 +3,7 @@
 // kernels in k0_precompute.cu / k1_stage.cu / k2_wall.cu.
 #include <dlfcn.h>
 #include <nccl.h>  // types only; the library is resolved at run time
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges show up in nsys / ncu --nvtx
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -19,6 +20,9 @@ void vh_set_error(const char* fmt, ...) {
 }
 
 namespace {
+
+inline void nvtx_push(const char* name) { nvtxRangePushA(name); }
+inline void nvtx_pop() { nvtxRangePop(); }
 
 struct NcclApi {
     void* lib = nullptr;
@@ -164,6 +168,7 @@ int vh_destroy(vh_handle* h) {
     cudaDeviceSynchronize();
     vh_nccl_destroy(h);
     k_free_run_buffers(h);
+    compact_release(h);
     void* ptrs[] = {h->d_xyz, h->d_tets, h->d_facet_cell, h->d_facet_verts, h->d_bcell_parent, h->d_btopology,
                     h->d_bvert_parent, h->d_facet_local, h->d_bcell_local, h->d_blocal_soa, h->d_glam, h->d_normal,
                     h->d_area, h->d_work, h->d_m_lf, h->d_m_w, h->d_m_mat, h->d_facet_nodes, h->d_row, h->d_wall_slot, h->d_flush, h->d_scalar};
@@ -194,7 +199,10 @@ int vh_destroy(vh_handle* h) {
 int vh_set_mesh(vh_handle* h, const double* xyz, int64_t nv, const int64_t* tets, int64_t nc) {
     VH_CHECK(h, VH_ERR_ARG, "vh_set_mesh: null handle");
     VH_CUDA(cudaSetDevice(h->device));
-    return k0_build_mesh(h, xyz, nv, tets, nc);
+    nvtx_push("K0 mesh precompute");
+    const int rc = k0_build_mesh(h, xyz, nv, tets, nc);
+    nvtx_pop();
+    return rc;
 }
 
 int vh_set_velocity_layout(vh_handle* h, int order, const double* refined_xyz, int64_t n_nodes, double tol,
@@ -220,7 +228,10 @@ int vh_set_velocity_layout(vh_handle* h, int order, const double* refined_xyz, i
     for (int c = 1; c < 3; ++c) top = comp_offset[c] > top ? comp_offset[c] : top;
     h->vec_len = top + max_slot + 1;  // doubles per snapshot vector that the gather can touch
     k_free_run_buffers(h);
-    return k0_build_velocity_map(h, order, refined_xyz, n_nodes, tol, node_perm, n_slots);
+    nvtx_push("K0 velocity map");
+    const int rc = k0_build_velocity_map(h, order, refined_xyz, n_nodes, tol, node_perm, n_slots);
+    nvtx_pop();
+    return rc;
 }
 
 int vh_get_sizes(vh_handle* h, int64_t n[7]) {
@@ -284,7 +295,8 @@ int vh_begin(vh_handle* h, double mu, double dt) {
     h->count = 0;
     h->count_on_device = false;
     h->have_tau_last = false;
-    h->kernel_ms = h->h2d_ms = 0.0;
+    h->kernel_ms = h->h2d_ms = h->gather_ms = 0.0;
+    h->h2d_bytes = 0;
     // no memsets on the hot path: the first K3 of the loop overwrites the sums instead of adding to them, and
     // tau_last is only read after a launch has written it
     h->sums_pending_zero = true;
@@ -306,6 +318,7 @@ int vh_set_tuning(vh_handle* h, int64_t batch_snapshots, int64_t chunk_snapshots
             h->d_stage[i] = h->d_wss_stage[i] = nullptr;
         }
         h->stage_cap = h->wss_stage_cap = 0;
+        h->stage_row_bytes = 0;
         if (h->d_W) cudaFree(h->d_W);  // the staged block is re-sized on the next launch
         h->d_W = nullptr;
         h->w_ld = 0;
@@ -352,55 +365,85 @@ static int prev_mode_for(vh_handle* h, int flags, const char* who, int* mode) {
     return VH_OK;
 }
 
-int vh_push_snapshots_device(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_bytes, int flags,
-                             double* d_wss_out) {
-    VH_TRY(check_ready(h, "vh_push_snapshots_device"));
-    VH_CHECK(d_u && n_snap > 0, VH_ERR_ARG, "vh_push_snapshots_device: nothing to push");
-    VH_CHECK(stride_bytes % 8 == 0 && stride_bytes >= 8 * h->vec_len, VH_ERR_ARG,
-             "vh_push_snapshots_device: stride %lld smaller than a vector (%lld doubles)", (long long)stride_bytes,
-             (long long)h->vec_len);
+// Device-resident snapshots: whole vectors (K1 gathers the wall layer) or compact blocks (K1 transposes).
+static int push_device(vh_handle* h, const char* who, const double* d_u, int64_t n_snap, int64_t stride_bytes, int flags,
+                       double* d_wss_out, bool dense) {
+    VH_TRY(check_ready(h, who));
+    VH_CHECK(d_u && n_snap > 0, VH_ERR_ARG, "%s: nothing to push", who);
+    const int64_t row_elems = dense ? 3 * h->nWn_pad : h->vec_len;
+    VH_CHECK(stride_bytes % 8 == 0 && stride_bytes >= 8 * row_elems, VH_ERR_ARG,
+             "%s: stride %lld smaller than a %s (%lld doubles)", who, (long long)stride_bytes,
+             dense ? "compact block" : "vector", (long long)row_elems);
     int mode = 0;
-    VH_TRY(prev_mode_for(h, flags, "vh_push_snapshots_device", &mode));
+    VH_TRY(prev_mode_for(h, flags, who, &mode));
     const int64_t stride = stride_bytes / 8;
     VH_CHECK(mode != 2 || n_snap >= 2, VH_ERR_ARG, "halo push needs at least one real snapshot after the halo");
     const int64_t n_real = n_snap - (mode == 2 ? 1 : 0);
     if (d_wss_out && h->wss_ld > 0) {
         VH_CHECK(h->wss_col + n_real <= h->wss_ld, VH_ERR_ARG,
-                 "vh_push_snapshots_device: WSS matrix has %lld columns, %lld already written, %lld more pushed",
+                 "%s: WSS matrix has %lld columns, %lld already written, %lld more pushed", who,
                  (long long)h->wss_ld, (long long)h->wss_col, (long long)n_real);
         d_wss_out += h->wss_col;
         h->wss_col += n_real;
     }
-    return k2_launch(h, mode == 2 ? d_u + stride : d_u, n_real, stride, mode, d_wss_out, h->wss_ld);
+    return k2_launch(h, mode == 2 ? d_u + stride : d_u, n_real, stride, mode, d_wss_out, h->wss_ld, dense);
 }
 
-int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t stride_bytes, int flags, double* wss_out) {
-    VH_TRY(check_ready(h, "vh_push_snapshots"));
-    VH_CHECK(u && n_snap > 0, VH_ERR_ARG, "vh_push_snapshots: nothing to push");
-    const int64_t vec_bytes = 8 * h->vec_len;
-    VH_CHECK(stride_bytes % 8 == 0 && stride_bytes >= vec_bytes, VH_ERR_ARG,
-             "vh_push_snapshots: stride %lld smaller than a vector (%lld bytes)", (long long)stride_bytes,
-             (long long)vec_bytes);
+int vh_push_snapshots_device(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_bytes, int flags,
+                             double* d_wss_out) {
+    return push_device(h, "vh_push_snapshots_device", d_u, n_snap, stride_bytes, flags, d_wss_out, false);
+}
+
+int vh_push_compact_device(vh_handle* h, const double* d_c, int64_t n_snap, int64_t stride_bytes, int flags,
+                           double* d_wss_out) {
+    return push_device(h, "vh_push_compact_device", d_c, n_snap, stride_bytes, flags, d_wss_out, true);
+}
+
+// Host snapshots -> device, double buffered against the kernels.  Three sources:
+//   SRC_FULL     whole vectors cross the bus, K1 gathers the wall layer on the device
+//   SRC_GATHER   whole vectors in host memory, the wall layer is gathered on the host (compact.cu) piece by piece into
+//                a pinned ring while the previous piece crosses the bus; K1 transposes
+//   SRC_COMPACT  the caller already holds compact blocks (vh_compact_snapshots / vh_compact_rows)
+enum { SRC_FULL = 0, SRC_GATHER = 1, SRC_COMPACT = 2 };
+
+static int push_host(vh_handle* h, const char* who, const double* u, int64_t n_snap, int64_t stride_bytes, int flags,
+                     double* wss_out, int kind) {
+    VH_TRY(check_ready(h, who));
+    VH_CHECK(u && n_snap > 0, VH_ERR_ARG, "%s: nothing to push", who);
+    const bool dense = kind != SRC_FULL;
+    const int64_t row_elems = dense ? 3 * h->nWn_pad : h->vec_len;  // doubles per snapshot on the device
+    const int64_t row_bytes = 8 * row_elems;
+    const int64_t src_bytes = kind == SRC_COMPACT ? row_bytes : 8 * h->vec_len;
+    VH_CHECK(stride_bytes % 8 == 0 && stride_bytes >= src_bytes, VH_ERR_ARG,
+             "%s: stride %lld smaller than a %s (%lld bytes)", who, (long long)stride_bytes,
+             kind == SRC_COMPACT ? "compact block" : "vector", (long long)src_bytes);
     int mode = 0;
-    VH_TRY(prev_mode_for(h, flags, "vh_push_snapshots", &mode));
+    VH_TRY(prev_mode_for(h, flags, who, &mode));
     const bool halo = mode == 2;
     VH_CHECK(!halo || n_snap >= 2, VH_ERR_ARG, "halo push needs at least one real snapshot after the halo");
     const int64_t nF = h->nF;
     const bool wss_matrix = wss_out && h->wss_ld > 0;
     VH_CHECK(!wss_matrix || h->wss_col + n_snap - (halo ? 1 : 0) <= h->wss_ld, VH_ERR_ARG,
-             "vh_push_snapshots: WSS matrix has %lld columns, %lld already written, %lld more pushed",
+             "%s: WSS matrix has %lld columns, %lld already written, %lld more pushed", who,
              (long long)h->wss_ld, (long long)h->wss_col, (long long)(n_snap - (halo ? 1 : 0)));
 
     // stage capacity: user value, else half of the push -- the batches then shrink geometrically (1/2, 1/4, 1/8, 1/8):
     // large copies move faster over PCIe (55 GB/s for 72 MB in one piece against 52 for eight 9 MB pieces, measured),
     // a small last batch leaves little kernel time exposed behind the last copy; at least 32 snapshots per batch, at
     // most what fits in ~30 % of free memory / 2 buffers or 8 GiB
+    if (h->stage_cap != 0 && h->stage_row_bytes != row_bytes) {  // the other kind of source was pushed before
+        for (int i = 0; i < 2; ++i) {
+            if (h->d_stage[i]) cudaFree(h->d_stage[i]);
+            h->d_stage[i] = nullptr;
+        }
+        h->stage_cap = 0;
+    }
     if (h->stage_cap == 0) {
         int64_t cap = h->batch_snapshots;
         if (cap <= 0) {
             size_t free_b = 0, total_b = 0;
             VH_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            int64_t per_snap = vec_bytes + (wss_out ? 72 * nF : 0);
+            int64_t per_snap = row_bytes + (wss_out ? 72 * nF : 0);
             int64_t budget = (int64_t)(0.3 * (double)free_b) / 2;
             if (budget > (8LL << 30)) budget = 8LL << 30;
             cap = (n_snap + 1) / 2;
@@ -409,8 +452,9 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
             if (cap > n_snap) cap = n_snap;
         }
         if (cap < 2) cap = 2;
-        for (int i = 0; i < 2; ++i) VH_CUDA(cudaMalloc(&h->d_stage[i], (size_t)(cap * vec_bytes)));
+        for (int i = 0; i < 2; ++i) VH_CUDA(cudaMalloc(&h->d_stage[i], (size_t)(cap * row_bytes)));
         h->stage_cap = cap;
+        h->stage_row_bytes = row_bytes;
     }
     if (wss_out && h->wss_stage_cap < h->stage_cap) {
         for (int i = 0; i < 2; ++i) {
@@ -418,6 +462,16 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
             VH_CUDA(cudaMalloc(&h->d_wss_stage[i], (size_t)(h->stage_cap * 72 * nF)));
         }
         h->wss_stage_cap = h->stage_cap;
+    }
+    // gather pieces: at most ~32 MiB of compact blocks each (a few ms of bus time), and at least four per batch so
+    // that gathering, copying and computing overlap even inside a single batch
+    int64_t piece = 1;
+    if (kind == SRC_GATHER) {
+        piece = (32LL << 20) / row_bytes;
+        const int64_t quarter = (h->stage_cap + 3) / 4;
+        if (piece > quarter) piece = quarter;
+        if (piece < 1) piece = 1;
+        VH_TRY(compact_ring_ensure(h, piece * row_bytes));
     }
 
     // (h2d start, h2d stop, kernel start, kernel stop) per batch, from a pool that lives with the handle: creating
@@ -433,7 +487,7 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
         return VH_OK;
     };
     int64_t pos = 0, real_done = 0;
-    int b = 0;
+    int b = 0, ring = 0;
     bool first = true;
     int rc = VH_OK;
     while (pos < n_snap && rc == VH_OK) {
@@ -452,19 +506,38 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
         // copy stream: wait until the kernel that last read this buffer is done, then H2D
         cudaStreamWaitEvent(h->s_copy, h->ev_consumed[buf], 0);
         cudaEventRecord(c0, h->s_copy);
-        // contiguous rows (the usual case: one block of u.h5 vectors) go as one flat copy
-        cudaError_t ce =
-            stride_bytes == vec_bytes
-                ? cudaMemcpyAsync(h->d_stage[buf], (const char*)u + pos * stride_bytes, (size_t)(nb * vec_bytes),
-                                  cudaMemcpyHostToDevice, h->s_copy)
-                : cudaMemcpy2DAsync(h->d_stage[buf], (size_t)vec_bytes, (const char*)u + pos * stride_bytes,
-                                    (size_t)stride_bytes, (size_t)vec_bytes, (size_t)nb, cudaMemcpyHostToDevice,
-                                    h->s_copy);
+        cudaError_t ce = cudaSuccess;
+        if (kind == SRC_GATHER) {
+            nvtx_push("gather+h2d batch");
+            for (int64_t p0 = 0; p0 < nb && rc == VH_OK && ce == cudaSuccess; p0 += piece) {
+                const int64_t np = nb - p0 < piece ? nb - p0 : piece;
+                if (h->cstage_busy[ring]) cudaEventSynchronize(h->ev_cstage[ring]);  // its last copy has left the slot
+                rc = compact_gather(h, nullptr, (const double*)((const char*)u + (pos + p0) * stride_bytes),
+                                    stride_bytes / 8, np, h->h_cstage[ring], row_elems);
+                if (rc != VH_OK) break;
+                ce = cudaMemcpyAsync(h->d_stage[buf] + p0 * row_elems, h->h_cstage[ring], (size_t)(np * row_bytes),
+                                     cudaMemcpyHostToDevice, h->s_copy);
+                cudaEventRecord(h->ev_cstage[ring], h->s_copy);
+                h->cstage_busy[ring] = true;
+                ring = (ring + 1) % 3;
+            }
+            nvtx_pop();
+            if (rc != VH_OK) break;
+        } else {
+            // contiguous rows (the usual case: one block of u.h5 vectors) go as one flat copy
+            ce = stride_bytes == row_bytes
+                     ? cudaMemcpyAsync(h->d_stage[buf], (const char*)u + pos * stride_bytes, (size_t)(nb * row_bytes),
+                                       cudaMemcpyHostToDevice, h->s_copy)
+                     : cudaMemcpy2DAsync(h->d_stage[buf], (size_t)row_bytes, (const char*)u + pos * stride_bytes,
+                                         (size_t)stride_bytes, (size_t)row_bytes, (size_t)nb, cudaMemcpyHostToDevice,
+                                         h->s_copy);
+        }
         if (ce != cudaSuccess) {
-            vh_set_error("vh_push_snapshots: H2D copy failed: %s", cudaGetErrorString(ce));
+            vh_set_error("%s: H2D copy failed: %s", who, cudaGetErrorString(ce));
             rc = VH_ERR_CUDA;
             break;
         }
+        h->h2d_bytes += nb * row_bytes;
         cudaEventRecord(c1, h->s_copy);
         cudaEventRecord(h->ev_copied[buf], h->s_copy);
         // compute stream
@@ -474,13 +547,13 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
         int64_t n_real = nb;
         int pm = first ? mode : 1;
         if (first && halo) {
-            d_u += h->vec_len;
+            d_u += row_elems;
             n_real = nb - 1;
         }
         cudaEventRecord(k0, h->s_compute);
         // per-snapshot vectors, or a (9 nF) x stage_cap time-major block whose first n_real columns are copied out
-        rc = k2_launch(h, d_u, n_real, h->vec_len, pm, wss_out ? h->d_wss_stage[buf] : nullptr,
-                       wss_matrix ? h->stage_cap : 0);
+        rc = k2_launch(h, d_u, n_real, row_elems, pm, wss_out ? h->d_wss_stage[buf] : nullptr,
+                       wss_matrix ? h->stage_cap : 0, dense);
         cudaEventRecord(k1, h->s_compute);
         cudaEventRecord(h->ev_consumed[buf], h->s_compute);
         if (rc == VH_OK && wss_out && n_real > 0) {
@@ -494,7 +567,7 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
                      : cudaMemcpyAsync(wss_out + real_done * 9 * nF, h->d_wss_stage[buf], (size_t)(n_real * 72 * nF),
                                        cudaMemcpyDeviceToHost, h->s_d2h);
             if (ce != cudaSuccess) {
-                vh_set_error("vh_push_snapshots: D2H copy failed: %s", cudaGetErrorString(ce));
+                vh_set_error("%s: D2H copy failed: %s", who, cudaGetErrorString(ce));
                 rc = VH_ERR_CUDA;
             }
             cudaEventRecord(h->ev_wss[buf], h->s_d2h);
@@ -507,9 +580,10 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
     if (wss_matrix) h->wss_col += real_done;
     cudaError_t e1 = cudaStreamSynchronize(h->s_copy), e2 = cudaStreamSynchronize(h->s_compute);
     const cudaError_t e3 = cudaStreamSynchronize(h->s_d2h);
+    for (int i = 0; i < 3; ++i) h->cstage_busy[i] = false;  // the copy stream has drained
     if (e1 == cudaSuccess) e1 = e3;
     if (rc == VH_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
-        vh_set_error("vh_push_snapshots: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        vh_set_error("%s: %s", who, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
         rc = VH_ERR_CUDA;
     }
     for (size_t i = 0; i + 3 < ev_used && rc == VH_OK; i += 4) {
@@ -519,6 +593,64 @@ int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t str
         if (cudaEventElapsedTime(&ms, evs[i + 2], evs[i + 3]) == cudaSuccess) h->kernel_ms += ms;
     }
     return rc;
+}
+
+int vh_push_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t stride_bytes, int flags, double* wss_out) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_push_snapshots: null handle");
+    return push_host(h, "vh_push_snapshots", u, n_snap, stride_bytes, flags, wss_out,
+                     h->order != 0 && compact_wanted(h) ? SRC_GATHER : SRC_FULL);
+}
+
+int vh_push_compact(vh_handle* h, const double* c, int64_t n_snap, int64_t stride_bytes, int flags, double* wss_out) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_push_compact: null handle");
+    return push_host(h, "vh_push_compact", c, n_snap, stride_bytes, flags, wss_out, SRC_COMPACT);
+}
+
+// ---- wall-layer compaction (host side, compact.cu) ------------------------------------------------------------------
+int vh_set_host_compaction(vh_handle* h, int mode, int threads) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_set_host_compaction: null handle");
+    VH_CHECK(mode >= 0 && mode <= 2 && threads >= 0, VH_ERR_ARG, "vh_set_host_compaction: mode 0|1|2, threads >= 0");
+    h->compact_mode = mode;
+    if (threads != h->host_threads) {
+        h->host_threads = threads;
+        compact_release(h);  // the pool is re-made with the new size on the next gather
+    }
+    return VH_OK;
+}
+
+int vh_get_compact_info(vh_handle* h, int64_t* compact_len, int* active) {
+    VH_CHECK(h && h->order != 0, VH_ERR_ARG, "vh_get_compact_info: call vh_set_velocity_layout first");
+    if (compact_len) *compact_len = 3 * h->nWn_pad;
+    if (active) *active = compact_wanted(h) ? 1 : 0;
+    return VH_OK;
+}
+
+int vh_get_wall_slots(vh_handle* h, int64_t* slots) {
+    VH_CHECK(h && h->order != 0 && slots, VH_ERR_ARG, "vh_get_wall_slots: call vh_set_velocity_layout first");
+    for (int64_t i = 0; i < h->nWn; ++i) slots[i] = h->h_wall_slot[(size_t)i];
+    return VH_OK;
+}
+
+int vh_compact_snapshots(vh_handle* h, const double* u, int64_t n_snap, int64_t stride_bytes, double* out) {
+    VH_CHECK(h && h->order != 0, VH_ERR_ARG, "vh_compact_snapshots: call vh_set_velocity_layout first");
+    VH_CHECK(u && out && n_snap > 0, VH_ERR_ARG, "vh_compact_snapshots: null argument");
+    VH_CHECK(stride_bytes % 8 == 0 && stride_bytes >= 8 * h->vec_len, VH_ERR_ARG,
+             "vh_compact_snapshots: stride %lld smaller than a vector (%lld bytes)", (long long)stride_bytes,
+             (long long)(8 * h->vec_len));
+    return compact_gather(h, nullptr, u, stride_bytes / 8, n_snap, out, 3 * h->nWn_pad);
+}
+
+int vh_compact_rows(vh_handle* h, const double* const* rows, int64_t n_snap, double* out) {
+    VH_CHECK(h && h->order != 0, VH_ERR_ARG, "vh_compact_rows: call vh_set_velocity_layout first");
+    VH_CHECK(rows && out && n_snap > 0, VH_ERR_ARG, "vh_compact_rows: null argument");
+    return compact_gather(h, rows, nullptr, 0, n_snap, out, 3 * h->nWn_pad);
+}
+
+int vh_get_io_stats(vh_handle* h, double* gather_ms, int64_t* h2d_bytes) {
+    VH_CHECK(h, VH_ERR_ARG, "vh_get_io_stats: null handle");
+    if (gather_ms) *gather_ms = h->gather_ms;
+    if (h2d_bytes) *h2d_bytes = h->h2d_bytes;
+    return VH_OK;
 }
 
 int vh_get_sums(vh_handle* h, double* sums, int64_t* count) {
@@ -858,7 +990,12 @@ int vh_peer_init(vh_handle* h) {
         peer_close(h);
         return rc;
     }
-    h->peer_epoch = 0;
+    // The arrival counters in d_sums_block are only zeroed at allocation, so a second vh_peer_init (new communicator,
+    // same engine) must not restart the epochs below values the counters already hold: every rank continues from the
+    // largest epoch any rank has used.
+    double ep = (double)h->peer_epoch;
+    VH_TRY(vh_nccl_allreduce_max(h, &ep));
+    h->peer_epoch = (uint64_t)(ep + 0.5);
     h->peer_ready = true;
     return VH_OK;
 }

@@ -112,6 +112,18 @@ struct vh_handle {
     // wall-layer nodes = velocity nodes referenced by any wall cell, ascending in vector position
     int64_t nWn = 0, nWn_pad = 0;      // padded to a multiple of 32 (padding repeats the last node)
     int32_t* d_wall_slot = nullptr;    // [nWn_pad] element offset of the node inside a snapshot vector
+    std::vector<int32_t> h_wall_slot;  // host copy (nWn_pad entries) for the host-side wall-layer compaction
+    // Wall-layer compaction in front of PCIe (compact.cu): a snapshot travels as the dense block C[c][i] =
+    // vec[comp_offset[c] + wall_slot[i]] (3 * nWn_pad doubles) instead of the whole vector; K1 is then a pure transpose.
+    int compact_mode = 0;              // 0 auto (by nWn_pad / vector slots), 1 never, 2 always
+    int host_threads = 0;              // gather threads (0: auto)
+    double* h_cstage[3] = {nullptr, nullptr, nullptr};  // pinned ring of gathered pieces
+    int64_t cstage_bytes = 0;          // bytes per ring slot
+    cudaEvent_t ev_cstage[3] = {nullptr, nullptr, nullptr};  // H2D out of the slot has completed
+    bool cstage_busy[3] = {false, false, false};
+    void* host_pool = nullptr;         // HostPool* (compact.cu)
+    double gather_ms = 0.0;            // host time spent gathering since vh_begin
+    int64_t h2d_bytes = 0;             // bytes copied host -> device since vh_begin
     // K1 output: W[((wall node * (w_ld / 32) + column / 32) * 3 + component) * 32 + column % 32], columns = snapshots
     // of the current launch (time tiles of 32, 768 contiguous bytes per node and tile)
     double* d_W = nullptr;
@@ -139,6 +151,7 @@ struct vh_handle {
     // programmatic stream serialization per kernel: bit 0 K1, bit 1 K2, bit 2 K3 (VASP_B200_PDL).  Measured (profiles/
     // r1pdl): K1 + K2 is the best mask (55.8 us per headline step against 64 without); adding K3 costs 30 us on P2.
     int pdl = 11;                  // bit 3: the fused peer reduction after K3 (2 GPUs, headline: 72.4 -> 70.3 us per step)
+    bool k2_configured[2] = {false, false};  // cudaFuncSetAttribute done on this handle's device (P1, P2)
     bool peer_unchecked = false;   // a fused reduction was enqueued and its "peer lost" word not looked at yet
     double* peer_block[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double* d_tau_last[2] = {nullptr, nullptr};  // [9][nF], ping-pong (read by first chunk, written by last)
@@ -155,6 +168,7 @@ struct vh_handle {
     // staging (double buffered)
     double* d_stage[2] = {nullptr, nullptr};
     int64_t stage_cap = 0;  // snapshots per stage buffer
+    int64_t stage_row_bytes = 0;  // bytes per snapshot the stage buffers were sized for (whole vector | compact block)
     double* d_wss_stage[2] = {nullptr, nullptr};
     int64_t wss_stage_cap = 0;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_wss[2] = {nullptr, nullptr};
@@ -185,14 +199,15 @@ int k0_build_velocity_map(vh_handle* h, int order, const double* refined_xyz, in
 // ---- K1 (k1_stage.cu) ------------------------------------------------------------------------------------------------
 // W[((i * (w_ld / 32) + col / 32) * 3 + c) * 32 + col % 32] = u[col * stride_elems + comp_offset[c] + wall_slot[i]]
 // for col < ncol, i < nWn_pad (zero up to the next multiple of 32 columns)
-int k1_launch(vh_handle* h, const double* d_u, int64_t ncol, int64_t stride_elems);
+// dense: d_u holds compact blocks (u[col * stride + c * nWn_pad + i]); K1 is then a pure transpose
+int k1_launch(vh_handle* h, const double* d_u, int64_t ncol, int64_t stride_elems, bool dense);
 
 // ---- K2/K3/K4 (k2_wall.cu) ---------------------------------------------------------------------------------------
 // `n_snap` resident snapshots (d_u + s * stride_elems), staged (K1) and reduced (K2, K3) in column blocks.
 // prev_mode: 0 tau_prev=0, 1 tau_prev from h->d_tau_last, 2 recompute from the snapshot just before d_u (halo).
 // d_wss (may be null): [n_snap][nF][9] if wss_ld == 0, else the (9 nF) x wss_ld time-major matrix (columns 0..n_snap).
 int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_elems, int prev_mode, double* d_wss,
-              int64_t wss_ld);
+              int64_t wss_ld, bool dense = false);
 int k4_finalize(vh_handle* h, int64_t n_total, double* d_out5);  // d_out5: 5 arrays [nF*3] TAWSS,OSI,RRT,ECAP,TWSSG
 // Fused cross-GPU reduction + final formulas: waits until every rank has signalled `epoch`, adds the partial sums of
 // all ranks in rank order straight from their memory (NVLink peer loads), writes the reduced sums and the indices.
@@ -204,3 +219,11 @@ int k4_peer_reduce_finalize(vh_handle* h, const PeerBlocks& pb, int64_t half_off
 int k_free_run_buffers(vh_handle* h);
 
 FacetTables vh_tables(const vh_handle* h);
+
+// ---- host-side wall-layer compaction (compact.cu) ------------------------------------------------------------------
+// out[r * out_stride + c * nWn_pad + i] = rows[r][comp_offset[c] + wall_slot[i]] for r < n, on the handle's thread pool
+int compact_gather(vh_handle* h, const double* const* rows, const double* base, int64_t stride_elems, int64_t n,
+                   double* out, int64_t out_stride_elems);
+void compact_release(vh_handle* h);  // thread pool + pinned ring
+int compact_ring_ensure(vh_handle* h, int64_t slot_bytes);
+bool compact_wanted(const vh_handle* h);

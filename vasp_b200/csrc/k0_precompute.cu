@@ -186,7 +186,7 @@ __global__ void k0_rank_exterior(const int32_t* __restrict__ tets, int64_t nface
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// geometry + boundary mesh (dolfin BoundaryComputation: orientation swap, first-encounter vertex numbering)
+// geometry + boundary mesh (dolfin BoundaryComputation's first-encounter vertex numbering, then Mesh.order())
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void k0_geometry(const double* __restrict__ xyz, const int32_t* __restrict__ tets, int64_t nF,
                             const int32_t* __restrict__ facet_cell, const int8_t* __restrict__ facet_local,
@@ -241,13 +241,7 @@ __global__ void k0_geometry(const double* __restrict__ xyz, const int32_t* __res
     }
     double nx = a1[1] * a2[2] - a1[2] * a2[1], ny = a1[2] * a2[0] - a1[0] * a2[2], nz = a1[0] * a2[1] - a1[1] * a2[0];
     area[f] = 0.5 * sqrt(nx * nx + ny * ny + nz * nz);
-    // BoundaryComputation::reorder: swap the first two vertices if (p1-p0)x(p2-p0) points to the opposite vertex
-    double dotp = nx * (p[lv[0]][0] - p[k][0]) + ny * (p[lv[0]][1] - p[k][1]) + nz * (p[lv[0]][2] - p[k][2]);
-    if (dotp < 0.0) {
-        int tmp = lv[0];
-        lv[0] = lv[1];
-        lv[1] = tmp;
-    }
+    // the boundary-cell vertex order is settled later (k0_order_bcells): BoundaryMesh(..., order=True) sorts it
     // facet-canonical labels for the hot loop: 0,1,2 = boundary-cell vertices, 3 = opposite vertex
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -285,10 +279,45 @@ __global__ void k0_number_bverts(const int32_t* __restrict__ facet_verts, const 
     }
 }
 
-__global__ void k0_btopology(const int32_t* __restrict__ bcell_parent, const int32_t* __restrict__ vnumber,
-                             int64_t n3, int32_t* __restrict__ btopology) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n3) btopology[i] = vnumber[bcell_parent[i]];
+// BoundaryMesh(mesh, "exterior") is built with dolfin's default order = True: after BoundaryComputation has numbered
+// the boundary vertices (first encounter), Mesh.order() sorts every boundary cell's vertices ascending in BOUNDARY
+// vertex number.  k0_geometry left the three facet vertices ascending in parent id; this kernel puts them (and
+// everything indexed by boundary dof: bcell_parent, bcell_local, the first three grad-lambda rows) in that order.
+__global__ void k0_order_bcells(const int32_t* __restrict__ vnumber, int64_t nF, int32_t* __restrict__ bcell_parent,
+                                int8_t* __restrict__ bcell_local, int8_t* __restrict__ blocal_soa,
+                                double* __restrict__ glam, int32_t* __restrict__ btopology) {
+    int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nF) return;
+    int32_t pv[3], bn[3];
+    int8_t lv[3];
+    double g[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        pv[j] = bcell_parent[3 * f + j];
+        bn[j] = vnumber[pv[j]];
+        lv[j] = bcell_local[3 * f + j];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) g[j][d] = glam[(int64_t)(3 * j + d) * nF + f];
+    }
+    int o[3] = {0, 1, 2};
+#define VH_OSWAP(x, y)                 \
+    if (bn[o[x]] > bn[o[y]]) {         \
+        int t__ = o[x];                \
+        o[x] = o[y];                   \
+        o[y] = t__;                    \
+    }
+    VH_OSWAP(0, 1) VH_OSWAP(1, 2) VH_OSWAP(0, 1)
+#undef VH_OSWAP
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int s = o[j];
+        bcell_parent[3 * f + j] = pv[s];
+        btopology[3 * f + j] = bn[s];
+        bcell_local[3 * f + j] = lv[s];
+        blocal_soa[(int64_t)j * nF + f] = lv[s];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) glam[(int64_t)(3 * j + d) * nF + f] = g[s][d];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -691,7 +720,8 @@ int k0_build_mesh(vh_handle* h, const double* xyz, int64_t nv, const int64_t* te
     VH_TRY(dev_alloc(&h->d_bvert_parent, h->nBV));
     // vnumber[v] reuses d_vcount (voff no longer needed after k0_rank_exterior)
     k0_number_bverts<<<nblk(3 * nF), TPB, 0, st>>>(h->d_facet_verts, d_head, d_pos, 3 * nF, h->d_bvert_parent, d_vcount);
-    k0_btopology<<<nblk(3 * nF), TPB, 0, st>>>(h->d_bcell_parent, d_vcount, 3 * nF, h->d_btopology);
+    k0_order_bcells<<<nblk(nF), TPB, 0, st>>>(d_vcount, nF, h->d_bcell_parent, h->d_bcell_local, h->d_blocal_soa, h->d_glam,
+                                              h->d_btopology);
 
     // work list: singles (ascending facet id, padded to a warp multiple with -1), then multi-facet-cell facets
     int32_t *d_is_multi = d_flag, *d_is_single = d_pos, *d_pos_multi = nullptr, *d_pos_single = nullptr;
@@ -832,6 +862,9 @@ int k0_build_velocity_map(vh_handle* h, int order, const double* refined_xyz, in
     }
     VH_CUDA(cudaGetLastError());
     VH_CUDA(cudaStreamSynchronize(st));
+    // host copy of the wall-layer slots: the host-side compaction in front of the bus gathers with it (compact.cu)
+    h->h_wall_slot.resize((size_t)h->nWn_pad);
+    VH_CUDA(cudaMemcpy(h->h_wall_slot.data(), h->d_wall_slot, sizeof(int32_t) * (size_t)h->nWn_pad, cudaMemcpyDeviceToHost));
     dev_free(d_flag); dev_free(d_pos); dev_free(d_cnt);
     dev_free(d_perm);
     h->launches += 5;

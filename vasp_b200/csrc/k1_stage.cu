@@ -29,6 +29,9 @@ __device__ __forceinline__ double ld_stream(const double* p) {
     return v;
 }
 
+// DENSE: u holds compact blocks (the host gathered the wall layer in front of the bus, compact.cu): node i of
+// component c sits at c * nWn_pad + i, so the "gather" is the identity and K1 a pure transpose of 256-byte runs.
+template <bool DENSE>
 __global__ void __launch_bounds__(TILE* ROWS)
     k1_stage(const double* __restrict__ u, int64_t stride, int ncol, const int32_t* __restrict__ wall_slot,
              int64_t off0, int64_t off1, int64_t off2, double* __restrict__ W, int64_t ntile) {
@@ -36,7 +39,7 @@ __global__ void __launch_bounds__(TILE* ROWS)
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int64_t node0 = (int64_t)blockIdx.x * TILE;
     const int col0 = blockIdx.y * TILE;
-    const int64_t slot = wall_slot[node0 + tx];
+    const int64_t slot = DENSE ? node0 + tx : (int64_t)wall_slot[node0 + tx];
     double v[TILE / ROWS][3];
 #pragma unroll
     for (int r = 0; r < TILE / ROWS; ++r) {
@@ -73,15 +76,20 @@ __global__ void __launch_bounds__(TILE* ROWS)
 
 }  // namespace
 
-int k1_launch(vh_handle* h, const double* d_u, int64_t ncol, int64_t stride_elems) {
+int k1_launch(vh_handle* h, const double* d_u, int64_t ncol, int64_t stride_elems, bool dense) {
     VH_CHECK(ncol > 0 && ncol <= h->w_ld, VH_ERR_ARG, "k1_launch: %lld columns do not fit the staged block (%lld)",
              (long long)ncol, (long long)h->w_ld);
     const int64_t gy = (ncol + 2 * TILE - 1) / (2 * TILE) * 2;  // zero-filled up to whole 64-column passes of K2
     VH_CHECK(gy <= 65535, VH_ERR_ARG, "k1_launch: too many snapshots in one block");
     dim3 grid((unsigned)(h->nWn_pad / TILE), (unsigned)gy), block(TILE, ROWS);
-    VH_CUDA(vh_launch_pdl(k1_stage, grid, block, 0, h->s_compute, (h->pdl & 1) && !h->profile, d_u, stride_elems, (int)ncol,
-                          (const int32_t*)h->d_wall_slot, h->comp_offset[0], h->comp_offset[1], h->comp_offset[2],
-                          h->d_W, h->w_ld / TILE));
+    const bool pdl = (h->pdl & 1) && !h->profile;
+    if (dense)
+        VH_CUDA(vh_launch_pdl(k1_stage<true>, grid, block, 0, h->s_compute, pdl, d_u, stride_elems, (int)ncol,
+                              (const int32_t*)nullptr, (int64_t)0, h->nWn_pad, 2 * h->nWn_pad, h->d_W, h->w_ld / TILE));
+    else
+        VH_CUDA(vh_launch_pdl(k1_stage<false>, grid, block, 0, h->s_compute, pdl, d_u, stride_elems, (int)ncol,
+                              (const int32_t*)h->d_wall_slot, h->comp_offset[0], h->comp_offset[1], h->comp_offset[2],
+                              h->d_W, h->w_ld / TILE));
     h->launches += 1;
     return VH_OK;
 }

@@ -803,6 +803,7 @@ int k_free_run_buffers(vh_handle* h) {
         h->d_stage[i] = h->d_wss_stage[i] = nullptr;
     }
     h->stage_cap = h->wss_stage_cap = 0;
+    h->stage_row_bytes = 0;
     if (h->d_W) cudaFree(h->d_W);
     h->d_W = nullptr;
     h->w_ld = 0;
@@ -859,14 +860,14 @@ SegPlan plan_segments(int64_t ncol, int64_t pass_cols, int64_t n_items, int64_t 
 }
 
 template <int ORDER>
-int launch_k2(const K2Args& a, cudaStream_t st, bool pdl) {
+int launch_k2(vh_handle* h, const K2Args& a, cudaStream_t st, bool pdl) {
     using L = K2Launch<ORDER>;
-    static bool configured = false;  // per instantiation
-    if (!configured && L::SMEM_BYTES > 0) {
+    // function attributes belong to the (function, device) pair: remembered per handle, i.e. per GPU
+    if (!h->k2_configured[ORDER - 1] && L::SMEM_BYTES > 0) {
         VH_CUDA(cudaFuncSetAttribute(k2_wall<ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES));
         VH_CUDA(cudaFuncSetAttribute(k2_wall<ORDER>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
-        configured = true;
+        h->k2_configured[ORDER - 1] = true;
     }
     const unsigned blocks = (unsigned)(a.multi.gx * a.multi.gy + a.single.gx * a.single.gy);
     VH_CUDA(vh_launch_pdl(k2_wall<ORDER>, dim3(blocks), dim3(32 * K2_WARPS), L::SMEM_BYTES, st, pdl, a));
@@ -884,7 +885,7 @@ int64_t env_int(const char* name, int64_t dflt) {
 }  // namespace
 
 int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_elems, int prev_mode, double* d_wss,
-              int64_t wss_ld) {
+              int64_t wss_ld, bool dense) {
     if (n_snap <= 0) return VH_OK;
     const int64_t nF = h->nF;
     VH_TRY(ensure_stage_block(h, n_snap + 1));
@@ -919,7 +920,7 @@ int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_el
         const bool prof = h->profile && h->prof_used + 3 <= h->prof_pool.size();
         const int pdl = h->profile ? 0 : h->pdl;  // events between the kernels would serialise them anyway
         if (prof) cudaEventRecord(h->prof_pool[h->prof_used], h->s_compute);
-        VH_TRY(k1_launch(h, d_u + (pos - halo) * stride_elems, ncol, stride_elems));
+        VH_TRY(k1_launch(h, d_u + (pos - halo) * stride_elems, ncol, stride_elems, dense));
         if (prof) cudaEventRecord(h->prof_pool[h->prof_used + 1], h->s_compute);
         K2Args a;
         a.T = vh_tables(h);
@@ -946,9 +947,9 @@ int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_el
         a.mu = h->mu;
         a.inv_dt = 1.0 / h->dt;
         if (h->order == 2)
-            VH_TRY(launch_k2<2>(a, h->s_compute, (pdl & 2) != 0));
+            VH_TRY(launch_k2<2>(h, a, h->s_compute, (pdl & 2) != 0));
         else
-            VH_TRY(launch_k2<1>(a, h->s_compute, (pdl & 2) != 0));
+            VH_TRY(launch_k2<1>(h, a, h->s_compute, (pdl & 2) != 0));
         h->launches += 1;
         if (prof) {
             cudaEventRecord(h->prof_pool[h->prof_used + 2], h->s_compute);

@@ -191,6 +191,78 @@ class HemoEngine:
         check(self._lib.vh_push_snapshots(self._h, _ptr(u), u.shape[0], stride, int(flags), _ptr(wss_out)))
         return wss_out
 
+    # ---- wall-layer compaction in front of the bus (include/vasp_hemo.h) ---------------------------------------------
+    def set_host_compaction(self, mode: str = "auto", threads: int = 0) -> None:
+        """``mode``: "auto" (gather the wall layer on the host when it is a small share of the vector), "off", "on"."""
+        check(self._lib.vh_set_host_compaction(self._h, {"auto": 0, "off": 1, "on": 2}[mode], int(threads)))
+
+    @property
+    def compact_len(self) -> int:
+        """Doubles per compact block: 3 components x the wall-layer node count rounded up to 32."""
+        n = C.c_int64()
+        check(self._lib.vh_get_compact_info(self._h, C.byref(n), None))
+        return int(n.value)
+
+    @property
+    def compaction_active(self) -> bool:
+        """Would :meth:`push` gather the wall layer on the host for the current layout and mode?"""
+        a = C.c_int()
+        check(self._lib.vh_get_compact_info(self._h, None, C.byref(a)))
+        return bool(a.value)
+
+    def wall_slots(self) -> np.ndarray:
+        """Element offset inside a snapshot vector of every wall-layer node (ascending), ``(n_wall_nodes,)`` int64."""
+        out = np.empty(self.n_wall_nodes, np.int64)
+        check(self._lib.vh_get_wall_slots(self._h, _ptr(out)))
+        return out
+
+    def compact(self, u: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Host gather of the wall layer: ``(n, >= vec_len)`` rows -> ``(n, compact_len)`` compact blocks."""
+        if u.dtype != np.float64 or u.ndim != 2 or u.strides[1] != 8 or u.shape[1] < self.vec_len:
+            raise ValueError("u must be a 2-D float64 array with contiguous rows of at least vec_len entries")
+        n, m = u.shape[0], self.compact_len
+        if out is None:
+            out = pinned_empty((n, m))
+        if out.dtype != np.float64 or not out.flags.c_contiguous or out.size < n * m:
+            raise ValueError("out must be C-contiguous float64 with n * compact_len entries")
+        stride = u.strides[0] if n > 1 else u.shape[1] * 8
+        check(self._lib.vh_compact_snapshots(self._h, _ptr(u), n, stride, _ptr(out)))
+        return out
+
+    def compact_rows(self, addresses: np.ndarray, out: np.ndarray) -> np.ndarray:
+        """Same for rows given by their host addresses (``uint64``), e.g. datasets inside an ``mmap`` of ``u.h5``."""
+        addresses = np.ascontiguousarray(addresses, dtype=np.uint64)
+        n, m = len(addresses), self.compact_len
+        if out.dtype != np.float64 or not out.flags.c_contiguous or out.size < n * m:
+            raise ValueError("out must be C-contiguous float64 with n * compact_len entries")
+        check(self._lib.vh_compact_rows(self._h, _ptr(addresses), n, _ptr(out)))
+        return out
+
+    def push_compact(self, c: np.ndarray, flags: int = 0, wss_out: Optional[np.ndarray] = None) -> Optional[np.ndarray]:
+        """:meth:`push` for ``(n, compact_len)`` compact blocks (ideally pinned)."""
+        m = self.compact_len
+        if c.dtype != np.float64 or c.ndim != 2 or c.strides[1] != 8 or c.shape[1] < m:
+            raise ValueError("c must be a 2-D float64 array with contiguous rows of at least compact_len entries")
+        n_real = c.shape[0] - (1 if flags & PUSH_HALO_FIRST else 0)
+        if wss_out is not None and getattr(self, "_wss_matrix", None) is None and (
+                wss_out.dtype != np.float64 or not wss_out.flags.c_contiguous or wss_out.size < n_real * self.nF * 9):
+            raise ValueError("wss_out must be C-contiguous float64 with n*nF*9 entries")
+        if getattr(self, "_wss_matrix", None) is not None:
+            wss_out = self._wss_matrix
+        stride = c.strides[0] if c.shape[0] > 1 else c.shape[1] * 8
+        check(self._lib.vh_push_compact(self._h, _ptr(c), c.shape[0], stride, int(flags), _ptr(wss_out)))
+        return wss_out
+
+    def push_compact_device(self, d_c: int, n_snap: int, stride_bytes: int, flags: int = 0, d_wss: int = 0) -> None:
+        """Asynchronous launch over compact blocks already resident in device memory."""
+        check(self._lib.vh_push_compact_device(self._h, C.c_void_p(d_c), int(n_snap), int(stride_bytes), int(flags),
+                                               C.c_void_p(d_wss or None)))
+
+    def io_stats(self) -> Dict[str, float]:
+        g, b = C.c_double(), C.c_int64()
+        check(self._lib.vh_get_io_stats(self._h, C.byref(g), C.byref(b)))
+        return {"gather_ms": g.value, "h2d_bytes": int(b.value)}
+
     def push_device(self, d_u: int, n_snap: int, stride_bytes: int, flags: int = 0, d_wss: int = 0) -> None:
         """Asynchronous launch over snapshots already resident in device memory (raw device addresses)."""
         check(self._lib.vh_push_snapshots_device(self._h, C.c_void_p(d_u), int(n_snap), int(stride_bytes), int(flags),
