@@ -131,37 +131,65 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
-def build_workload(name: str, n_snap: int, rank: int):
+def build_geometry(name: str):
+    """Mesh, velocity nodes and the spatial modes of the synthetic series."""
     w = WORKLOADS[name]
     mesh = synth.vessel_mesh(w["n"], w["m"], radius=2.0e-3, stenosis=w["stenosis"], bulge=w["bulge"], seed=1234)
     xyz, tets = mesh["xyz"], mesh["tets"]
+    new_id = None
     if w["order"] == 2:
-        points, _, _ = synth.p2_points(xyz, tets, seed=1234)
+        points, _, new_id = synth.p2_points(xyz, tets, seed=1234)
     else:
         points = xyz
     basis = synth.velocity_basis(points, seed=2024)
-    # weak scaling: rank r owns snapshots [r*n, (r+1)*n) of one long series, plus the halo snapshot before them
-    halo = 1 if rank > 0 else 0
-    dt = PERIOD / n_snap
-    _, coef = synth.velocity_coefficients(n_snap + halo, period=PERIOD, seed=2024, t0=(rank * n_snap - halo) * dt)
+    return dict(name=name, xyz=xyz, tets=tets, points=points, basis=basis, order=w["order"], desc=w["desc"],
+                new_id=new_id)
+
+
+def series_coefficients(n_snap: int, first: int, period_snaps: int):
+    """Mode coefficients of snapshots [first, first + n_snap) of one long series whose period is ``period_snaps``."""
+    dt = PERIOD / period_snaps  # same waveform as synth.velocity_coefficients, on the time grid all ranks share
+    t = dt * (first + np.arange(1, n_snap + 1))
+    rng = np.random.default_rng(2024 + 1)
+    phase = rng.uniform(0, 2 * np.pi, size=synth.N_MODES)
+    coef = np.empty((n_snap, synth.N_MODES))
+    coef[:, 0] = 1.0 + 0.6 * np.sin(2 * np.pi * t / PERIOD) + 0.3 * np.sin(4 * np.pi * t / PERIOD)
+    for k in range(1, synth.N_MODES):
+        coef[:, k] = 0.2 * np.sin(2 * np.pi * k * t / PERIOD + phase[k])
     coef[:, 0] *= 0.3  # m/s scale
-    return dict(xyz=xyz, tets=tets, points=points, basis=basis, coef=coef, dt=dt, halo=halo, order=w["order"],
-                desc=w["desc"])
+    return coef, dt
+
+
+def build_workload(name: str, n_snap: int, rank: int):
+    """Geometry + the coefficients of rank ``rank``'s snapshots under weak scaling: rank r owns snapshots
+    [r*n, (r+1)*n) of one long series, plus the halo snapshot before them."""
+    g = build_geometry(name)
+    halo = 1 if rank > 0 else 0
+    coef, dt = series_coefficients(n_snap + halo, rank * n_snap - halo, n_snap)
+    return dict(g, coef=coef, dt=dt, halo=halo)
+
+
+def oracle_for(wl):
+    """The restated reference on this workload (test infrastructure; only the CPU legs of the bench come here)."""
+    from oracle import c_oracle, hemo_oracle as ho
+    node_of_p2 = None
+    if wl["order"] == 2:
+        node_of_p2 = wl["new_id"]  # synth.p2_points numbers vertices then edge midpoints exactly as the oracle does
+        cn, edges = ho.p2_cell_nodes(wl["tets"][:64])
+        assert np.allclose(ho.p2_node_coordinates(wl["xyz"], edges)[cn[:, 4:]], 0.5 * (
+            wl["xyz"][cn[:, [2, 1, 1, 0, 0, 0]]] + wl["xyz"][cn[:, [3, 3, 2, 3, 2, 1]]]))
+    stress = ho.SurfaceStress(wl["xyz"], wl["tets"], MU, wl["order"], node_of_p2)
+    return stress, c_oracle.COracle(stress), c_oracle.max_threads()
 
 
 def run_reference(args, rank: int, world: int) -> None:
     """CPU arm: the restated reference algorithm (oracle/hemo_oracle.c, all host threads) on the same workload."""
     if rank != 0:
         return
-    from oracle import c_oracle, hemo_oracle as ho
+    from oracle import hemo_oracle as ho
     wl = build_workload(args.workload, args.snapshots, 0)
-    stress = ho.SurfaceStress(wl["xyz"], wl["tets"], MU, wl["order"],
-                              None if wl["order"] == 1 else ho.match_points(
-                                  ho.p2_node_coordinates(wl["xyz"], ho.p2_cell_nodes(wl["tets"])[1]), wl["points"],
-                                  1e-8 * float(np.ptp(wl["points"], axis=0).max())))
-    co = c_oracle.COracle(stress)
+    stress, co, threads = oracle_for(wl)
     n = len(wl["points"])
-    threads = c_oracle.max_threads()
     # bounded sample: at most ~2 s of work per step
     n_s = min(args.snapshots, max(threads, int(2.0e6 * threads / max(stress.nF, 1))))
     u = synth.velocity_series(wl["basis"], wl["coef"][:n_s])
@@ -177,71 +205,104 @@ def run_reference(args, rank: int, world: int) -> None:
     sample = f"{n_s} of {args.snapshots} snapshots x {stress.nF} facets per step"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {wl['desc']}", "facets": stress.nF,
-                       "snapshots_per_gpu": args.snapshots, "order": wl["order"]},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.workload, wl, stress.nF, args.snapshots, world, args.scaling),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference = FEniCS path restated in C (oracle/hemo_oracle.c); dolfin itself is not installable"}
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args, rank: int, local_rank: int, world: int) -> None:
+def workload_config(name, wl, nF, n_snap, world, scaling):
+    """The keys both arms of the bench share (the driver compares them)."""
+    return {"workload": f"{name}: {wl['desc']}", "facets": int(nF), "snapshots_per_gpu": int(n_snap),
+            "order": int(wl["order"]), "tets": int(len(wl["tets"])), "velocity_nodes": int(len(wl["points"])),
+            "parallelism": f"time-shard x{world}", "scaling": scaling}
+
+
+def kernel_traffic(name: str):
+    """DRAM bytes per launch of K1 / K2 from the committed `ncu --set full` captures of this command."""
+    tfile = ROOT / "profiles" / "kernel_traffic.json"
+    try:
+        return json.loads(tfile.read_text()).get(name, {})
+    except Exception:
+        return {}
+
+
+def measure(name: str, n_res: int, n_e2e: int, args, rank: int, local_rank: int, world: int, headline: bool):
+    """One workload on this rank's GPU: device-resident pass (`value`), per-kernel pass (roofline), end-to-end pass from
+    pinned host vectors, CPU baseline.  Returns (entry dict, context) on rank 0, (None, context) elsewhere."""
     from vasp_b200.engine import HemoEngine, pinned_empty
-    from vasp_b200.timeshard import NcclComm
+    from vasp_b200.timeshard import NcclComm, plan_shard
 
-    wl = build_workload(args.workload, args.snapshots, rank)
-    n_snap, halo, order = args.snapshots, wl["halo"], wl["order"]
+    t_setup = time.perf_counter()
+    g = build_geometry(name)
+    order = g["order"]
     eng = HemoEngine(local_rank)
-    eng.set_mesh(wl["xyz"], wl["tets"])
-    if order == 2:
-        eng.set_velocity_layout(2, refined_xyz=wl["points"])
-    else:
-        eng.set_velocity_layout(1)
-    nF, vec_len = eng.nF, eng.vec_len
+    eng.set_mesh(g["xyz"], g["tets"])
+    eng.set_velocity_layout(order, refined_xyz=g["points"] if order == 2 else None)
+    if args.compaction != "auto":
+        eng.set_host_compaction(args.compaction)
+    nF, vec_len, n_nodes = eng.nF, eng.vec_len, len(g["points"])
     comm = NcclComm(eng, rank, world) if world > 1 else None
+    compact = eng.compaction_active
 
-    # inputs: pinned host copy (e2e) and resident device copies (value).  Timing rule: inputs must not be served from
-    # L2 across timed steps.  A workload smaller than 2x the 126 MB L2 gets enough rotating copies to exceed 2.5x L2
-    # (consecutive steps read different copies, so the K steps run back to back with no flush kernel and no host
-    # synchronisation in the timed region); larger workloads evict themselves.
-    u_host = pinned_empty((n_snap + halo, vec_len))
-    synth.velocity_series(wl["basis"], wl["coef"], out=u_host)
+    # this rank's snapshots of one long series: weak scaling gives every rank n_res snapshots (the series grows with
+    # the world), strong scaling splits n_res over the ranks; every rank but the first reads one halo snapshot
+    if args.scaling == "strong":
+        sh = plan_shard(n_res, rank, world)
+        first, n_mine, n_total, period = sh.start, sh.count, n_res, n_res
+    else:
+        first, n_mine, n_total, period = rank * n_res, n_res, n_res * world, n_res
+    halo = 1 if rank > 0 else 0
+    coef, dt = series_coefficients(n_mine + halo, first - halo, period)
+
+    # Resident input = what the product's host -> device path leaves in HBM for this workload: whole vectors (K1
+    # gathers the wall layer) or, when the wall layer is gathered in front of the bus, compact blocks (K1 transposes).
+    if compact:
+        slots = eng.wall_slots()  # blocked layout: slot == node number
+        nwp = eng.compact_len // 3
+        idx = np.concatenate([slots, np.full(nwp - len(slots), slots[-1])])
+        flat = np.ascontiguousarray(g["basis"][:, :, idx]).reshape(synth.N_MODES, 3 * nwp)
+        row_len = 3 * nwp
+    else:
+        flat = g["basis"].reshape(synth.N_MODES, 3 * n_nodes)
+        row_len = vec_len
+    resident_bytes = (n_mine + halo) * row_len * 8
+    # Timing rule: inputs must not be served from L2 across timed steps.  A workload smaller than 2x the 126 MB L2 gets
+    # enough rotating copies to exceed 2.5x L2 (consecutive steps read different copies, so the K steps run back to
+    # back with no flush kernel and no host synchronisation in the timed region); larger workloads evict themselves.
     L2 = 126e6
-    n_copies = 1 if u_host.nbytes >= 2 * L2 else min(8, int(np.ceil(2.5 * L2 / u_host.nbytes)))
-    d_copies = []
-    for _ in range(n_copies):
-        d = eng.device_alloc(u_host.nbytes)
-        eng.h2d(d, u_host)
-        d_copies.append(d)
+    n_copies = 1 if resident_bytes >= 2 * L2 else min(8, int(np.ceil(2.5 * L2 / resident_bytes)))
+    d_copies = [eng.device_alloc(resident_bytes) for _ in range(n_copies)]
+    chunk = max(1, int((256 << 20) // (row_len * 8)))
+    for a in range(0, n_mine + halo, chunk):  # synthesised and uploaded in pieces: 10 M tets x 256 snapshots = 6 GB
+        rows = coef[a:a + chunk] @ flat
+        for d in d_copies:
+            eng.h2d(d + a * row_len * 8, rows)
+    del flat
     flags = 2 if halo else 1
-    stride = vec_len * 8
-    n_total = n_snap * world
+    stride = row_len * 8
     step_no = [0]
 
     # --wss steps|matrix: K2 also writes tau of every snapshot (72 B per facet and snapshot), as one dolfin vector
     # per snapshot (WSS.h5) or as rows of the time-major matrix of the spectral tools (SURVEY.md §8f-2)
-    d_wss = eng.device_alloc(72 * nF * n_snap) if args.wss != "none" else 0
+    d_wss = eng.device_alloc(72 * nF * n_mine) if args.wss != "none" else 0
+    push_resident = eng.push_compact_device if compact else eng.push_device
 
     def step_resident():
         d_u = d_copies[step_no[0] % n_copies]
         step_no[0] += 1
-        eng.begin(MU, wl["dt"])
+        eng.begin(MU, dt)
         if args.wss == "matrix":
-            eng.set_wss_layout(n_snap, 0)
-        eng.push_device(d_u, n_snap + halo, stride, flags, d_wss)
+            eng.set_wss_layout(n_mine, 0)
+        push_resident(d_u, n_mine + halo, stride, flags, d_wss)
         if comm:
             comm.reduce_finalize(n_total, host=False)  # fused peer reduction + K4 (or ncclAllReduce + K4)
         else:
             eng.finalize_async(n_total)
 
-    def step_e2e():
-        eng.begin(MU, wl["dt"])
-        eng.push(u_host, flags=flags)
-        if comm:
-            return comm.reduce_finalize(n_total)
-        return eng.finalize(n_total)
-
+    steps = args.steps if headline else max(3, min(args.steps, args.other_steps))
     for _ in range(args.warmup):
         step_resident()
     eng.sync()
@@ -255,10 +316,15 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             step_resident()
         launches0 = eng.timers()["launches"]
         eng.timer_start()
-        for _ in range(args.steps):
+        for _ in range(steps):
             step_resident()
         total_ms = eng.timer_stop()  # CUDA events on the compute stream; stop synchronises
         launches1 = eng.timers()["launches"]
+        if total_ms < 25.0:  # a short timed region gets a second, untimed stretch so that NVML sees clocks under load
+            t_end = time.perf_counter() + 0.05
+            while time.perf_counter() < t_end:
+                step_resident()
+            eng.sync()
         # Same K steps once more with CUDA events between the kernels (per-launch K1/K2 durations for the roofline).
         # The events sit between dependent launches, so this pass runs without programmatic dependent launch and is a
         # few us per step slower than the pass above; `value` comes from the pass above.
@@ -269,122 +335,228 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             step_resident()
             eng.kernel_profile()  # drop the aligning step's events
         eng.timer_start()
-        for _ in range(args.steps):
+        for _ in range(steps):
             step_resident()
         total_ms_events = eng.timer_stop()
     if comm:
         comm.barrier()
-    k1_ms, k2_ms, k2_n = eng.kernel_profile()
+    k1_ms, k2_ms, k_n = eng.kernel_profile()
     eng.set_profile(False)
-    launches = launches1 - launches0  # k1 + k2 (+ k2 multi) + k3 + k4 per step (L2 flush not counted)
+    launches = launches1 - launches0  # k1 + k2 + k3 (+ k4 / the peer reduction) per step
     if comm:
         total_ms = comm.max(total_ms)
-    ms_per_step = total_ms / args.steps
-    value = world * nF * n_snap / (ms_per_step * 1e-3)
+    ms_per_step = total_ms / steps
+    value = n_total * nF / (ms_per_step * 1e-3) if args.scaling == "strong" else world * nF * n_mine / (ms_per_step * 1e-3)
 
-    # end to end through the public API: pinned host snapshots in, five result fields out
-    e2e_steps = max(1, min(args.steps, 10))
+    # parity of the reduced fields against the restated reference over the whole series (N > 1: SCALE lines carry it)
+    parity = None
+    if comm and args.parity and n_total * nF <= 2.0e9:
+        eng.begin(MU, dt)
+        push_resident(d_copies[0], n_mine + halo, stride, flags, 0)
+        fields = comm.reduce_finalize(n_total)
+        if rank == 0:
+            parity = parity_against_oracle(g, eng, fields, n_total, period, compact)
+    for d in d_copies + ([d_wss] if d_wss else []):
+        eng.device_free(d)
+
+    # end to end through the public API: pinned host snapshot VECTORS in, five result fields out
+    n_e2e = min(n_e2e, n_mine)
+    e2e_steps = max(1, min(steps, 10 if headline else 3))
     if os.environ.get("VASP_B200_E2E_BATCH"):  # experiments: snapshots per host->device batch (default: auto)
         eng.set_tuning(batch_snapshots=int(os.environ["VASP_B200_E2E_BATCH"]))
+    u_host = pinned_empty((n_e2e + halo, vec_len))
+    synth.velocity_series(g["basis"], coef[:n_e2e + halo], out=u_host)
+
+    def step_e2e():
+        eng.begin(MU, dt)
+        eng.push(u_host, flags=flags)
+        if comm:
+            return comm.reduce_finalize(n_e2e * world)
+        return eng.finalize(n_e2e)
+
     step_e2e()
     eng.sync()
     if comm:
         comm.barrier()
-    e2e_h2d_ms = e2e_kernel_ms = 0.0
+    e2e_h2d_ms = e2e_kernel_ms = e2e_gather_ms = 0.0
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         out = step_e2e()
-        tm = eng.timers()  # per time loop (vh_begin resets them): CUDA-event sums over the batches of the push
-        e2e_h2d_ms += tm["h2d_ms"] / e2e_steps        # copy stream
+        tm, st = eng.timers(), eng.io_stats()  # per time loop (vh_begin resets them)
+        e2e_h2d_ms += tm["h2d_ms"] / e2e_steps        # copy stream (includes waiting for gathered pieces)
         e2e_kernel_ms += tm["kernel_ms"] / e2e_steps  # compute stream (overlaps the copies)
+        e2e_gather_ms += st["gather_ms"] / e2e_steps  # host threads (overlap both)
+        h2d_bytes = st["h2d_bytes"]
     eng.sync()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     if comm:
         e2e_s = comm.max(e2e_s)
-    e2e_value = world * nF * n_snap / e2e_s
-    h2d_bytes = int((n_snap + halo) * vec_len * 8)
+    e2e_value = world * nF * n_e2e / e2e_s
     d2h_bytes = int(5 * 3 * nF * 8)
     osi = out["OSI"]
     sane = bool(np.isfinite(out["TAWSS"]).all() and np.nanmin(osi) >= -1e-12 and np.nanmax(osi) <= 0.5 + 1e-12)
-
     reduction = ("none" if not comm else "fused peer-memory reduce+finalize (NVLink, CUDA IPC)" if comm.fused
                  else "ncclAllReduce + finalize")
     if comm:
         comm.close()  # collective teardown while every rank is alive (rank 0 still has the JSON line to assemble)
-    for d in d_copies + ([d_wss] if d_wss else []):
-        eng.device_free(d)
+    ctx = dict(g=g, coef=coef, dt=dt, halo=halo, u_host=u_host, eng=eng, n_mine=n_mine)
     if rank != 0:
-        return
+        return None, ctx
+
     peak, peak_src = measured_peak_gbs()
     b_alg = algorithmic_bytes_per_unit(order, args.wss != "none")
-    units_per_launch = nF * n_snap
-    k2_avg_ms = k2_ms / max(k2_n, 1)
-    k1_avg_ms = k1_ms / max(k2_n, 1)
-    units_per_launch = units_per_launch * args.steps // max(k2_n, 1)  # a step may split into several column blocks
-    achieved = units_per_launch * b_alg / (k2_avg_ms * 1e-3) / 1e9
-    # K1 (staging) moves 8 B x 3 components per wall-layer node and snapshot, read once and written once
-    k1_bytes = 2 * 24 * eng.n_wall_nodes * (n_snap + halo) * args.steps / max(k2_n, 1)
-    # ... but a gather fetches whole 32-byte DRAM sectors: count the distinct sectors the wall-layer nodes occupy in a
-    # snapshot vector (the numbering of the synthetic meshes is randomly permuted on purpose, so a wall-layer node
-    # rarely shares its sector with another one)
-    wall_nodes = np.unique(eng.maps()["facet_nodes"])
-    n_all = len(wl["points"])
-    sectors = sum(np.unique((c * n_all + wall_nodes) // 4).size for c in range(3))
-    k1_sector_bytes = (32 * sectors + 24 * eng.n_wall_nodes) * (n_snap + halo) * args.steps / max(k2_n, 1)
-    traffic = None
-    tfile = ROOT / "profiles" / "k2_traffic.json"  # written from an `ncu --set full` capture of this command
-    if tfile.exists():
-        try:
-            traffic = json.loads(tfile.read_text()).get(args.workload, {}).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(wl, n_snap)
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "ms_per_step_with_kernel_events": total_ms_events / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['desc']}", "facets": nF, "snapshots_per_gpu": n_snap,
-                   "order": order, "wss_output": args.wss, "velocity_nodes": int(len(wl["points"])), "wall_layer_nodes": eng.n_wall_nodes,
-                   "tets": int(len(wl["tets"])),
-                   "parallelism": f"time-shard x{world}",
-                   "reduction": reduction, 
-                   "l2": (f"{n_copies} rotating resident copies of the input ({n_copies * u_host.nbytes / 1e6:.0f} MB > "
-                          f"2.5 x 126 MB L2), steps back to back" if n_copies > 1 else
-                          f"input {u_host.nbytes / 1e6:.0f} MB per step, larger than 2 x 126 MB L2"),
-                   "results_sane": sane},
+    launches_per_step = max(k_n, 1) / steps  # a step may split into several column blocks
+    cols = (n_mine + halo) / launches_per_step
+    units_per_launch = nF * n_mine / launches_per_step
+    k2_avg_ms, k1_avg_ms = k2_ms / max(k_n, 1), k1_ms / max(k_n, 1)
+    nW = eng.n_wall_nodes
+    traffic = kernel_traffic(name)
+    kernels = {}
+    # K2: the §8d figure -- 8 B x 3 components x (4 | 10) cell dofs per facet and snapshot (+72 B with the WSS series)
+    k2_bytes = units_per_launch * b_alg
+    # K1 moves 8 B x 3 components per wall-layer node and snapshot, read once and written once
+    k1_bytes = 2 * 24 * nW * cols
+    for kname, ms, nbytes in ((f"k2_wall<{order}>", k2_avg_ms, k2_bytes),
+                              ("k1_stage<dense>" if compact else "k1_stage<gather>", k1_avg_ms, k1_bytes)):
+        tr = traffic.get(kname.split("<")[0], {})
+        dram = tr.get("dram_bytes_per_launch") if abs(tr.get("columns", -1) - cols) < 0.5 else None
+        kernels[kname] = {"ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes,
+                          "achieved": nbytes / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                          "frac": nbytes / (ms * 1e-3) / 1e9 / peak if ms > 0 else None,
+                          "dram_bytes_per_launch": dram,
+                          "frac_dram": dram / (ms * 1e-3) / 1e9 / peak if dram and ms > 0 else None,
+                          "traffic_source": tr.get("source") if dram else None}
+    if not compact:
+        # a gather fetches whole 32-byte DRAM sectors: count the distinct sectors the wall-layer nodes occupy in a
+        # snapshot vector (the synthetic meshes are randomly renumbered on purpose)
+        wall_nodes = eng.wall_slots()
+        sectors = sum(np.unique((c * n_nodes + wall_nodes) // 4).size for c in range(3))
+        sb = (32 * sectors + 24 * nW) * cols
+        kernels["k1_stage<gather>"].update(sector_bytes_per_launch=sb,
+                                           frac_sectors=sb / (k1_avg_ms * 1e-3) / 1e9 / peak if k1_avg_ms > 0 else None)
+    dominant = max(kernels, key=lambda k: kernels[k]["ms_per_launch"])
+    dk = kernels[dominant]
+    cpu = cpu_baseline(dict(g, coef=coef, dt=dt, halo=halo), n_mine) if world == 1 and not args.no_cpu_baseline else None
+    entry = {
+        "workload": name, "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps,
+        "ms_per_step_with_kernel_events": total_ms_events / steps,
+        "config": dict(workload_config(name, g, nF, n_mine, world, args.scaling), wss_output=args.wss,
+                       wall_layer_nodes=nW, reduction=reduction,
+                       resident_input=("compact blocks (wall layer gathered in front of the bus): "
+                                       f"{row_len * 8 / 1e6:.2f} MB per snapshot" if compact else
+                                       f"whole snapshot vectors: {row_len * 8 / 1e6:.2f} MB per snapshot"),
+                       l2=(f"{n_copies} rotating resident copies of the input ({n_copies * resident_bytes / 1e6:.0f} MB "
+                           f"> 2.5 x 126 MB L2), steps back to back" if n_copies > 1 else
+                           f"input {resident_bytes / 1e6:.0f} MB per step, larger than 2 x 126 MB L2"),
+                       results_sane=sane, setup_s=round(time.perf_counter() - t_setup, 1)),
         "clocks": clk.summary(),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps, "h2d_ms_per_step": e2e_h2d_ms,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps, "snapshots": n_e2e,
+                "host_vector_bytes_per_step": int((n_e2e + halo) * vec_len * 8),
+                "bus": "wall layer gathered on the host, compact blocks copied" if compact else "whole vectors copied",
+                "copy_stream_ms_per_step": e2e_h2d_ms, "host_gather_ms_per_step": e2e_gather_ms,
                 "h2d_gbs": h2d_bytes / (e2e_h2d_ms * 1e-3) / 1e9 if e2e_h2d_ms > 0 else None,
                 "kernel_ms_per_step": e2e_kernel_ms},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": f"k2_wall<{order}>", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dk["achieved"], "peak": peak, "unit": "GB/s",
+                     "frac": dk["frac"], "traffic": dk["dram_bytes_per_launch"], "peak_source": peak_src,
+                     "frac_dram": dk["frac_dram"],
+                     # whole step (K1 + K2 + K3 ...) on the §8d algorithmic bytes: the figure to read first
+                     "frac_step": nF * n_mine * b_alg / (ms_per_step * 1e-3) / 1e9 / peak,
                      "algorithmic_bytes_per_unit": b_alg, "units_per_launch": units_per_launch,
-                     "kernel_ms_per_launch": k2_avg_ms, "launches_timed": k2_n,
-                     "stage_kernel": {"kernel": "k1_stage", "ms_per_launch": k1_avg_ms,
-                                      "bytes_per_launch": k1_bytes,
-                                      "achieved": k1_bytes / (k1_avg_ms * 1e-3) / 1e9 if k1_avg_ms > 0 else None,
-                                      "frac": k1_bytes / (k1_avg_ms * 1e-3) / 1e9 / peak if k1_avg_ms > 0 else None,
-                                      "wall_nodes": eng.n_wall_nodes,
-                                      "sector_bytes_per_launch": k1_sector_bytes,
-                                      "frac_sectors": (k1_sector_bytes / (k1_avg_ms * 1e-3) / 1e9 / peak
-                                                       if k1_avg_ms > 0 else None)}},
+                     "columns_per_launch": cols, "launches_timed": k_n, "kernels": kernels},
         "cpu_baseline": cpu,
     }
-    if world == 1 and not args.no_io_leg:
+    if parity is not None:
+        entry["parity_rel_l2"] = parity
+    return entry, ctx
+
+
+def parity_against_oracle(g, eng, fields, n_total: int, period: int, compact: bool):
+    """max over the five fields of the relative L2 distance between the cross-GPU result and the restated reference
+    run over the WHOLE series on the host (chunked; the oracle reads the same container the GPUs were given)."""
+    from oracle import c_oracle, hemo_oracle as ho
+    wl = dict(g)
+    stress, co, threads = oracle_for(wl)
+    n_nodes = len(g["points"])
+    if compact:
+        slots = eng.wall_slots()
+        nwp = eng.compact_len // 3
+        flat = np.ascontiguousarray(g["basis"][:, :, slots]).reshape(synth.N_MODES, 3, len(slots))
+        pad = np.zeros((synth.N_MODES, 3, nwp))
+        pad[:, :, :len(slots)] = flat
+        flat = pad.reshape(synth.N_MODES, 3 * nwp)
+        remap = np.searchsorted(slots, stress.maps.cell_nodes[stress.maps.wall_cells])
+        co._keep["wall_nodes"] = np.ascontiguousarray(remap, dtype=np.int64)
+        co._maps.wall_nodes = co._keep["wall_nodes"].ctypes.data
+        off = (0, nwp, 2 * nwp)
+    else:
+        flat = g["basis"].reshape(synth.N_MODES, 3 * n_nodes)
+        off = (0, n_nodes, 2 * n_nodes)
+    chunk = max(2, int((512 << 20) // (flat.shape[1] * 8)))
+    sums, prev, dt = None, None, None
+    for a in range(0, n_total, chunk):
+        coef, dt = series_coefficients(min(chunk, n_total - a), a, period)
+        r = co.run(coef @ flat, dt, off, tau_prev=prev, threads=threads)
+        prev = r["tau_last"]
+        sums = r if sums is None else {k: (sums[k] + r[k] if k != "tau_last" else r[k]) for k in r}
+    fin = ho.finalize(sums["wss_sum"], sums["tawss_sum"], sums["twssg_sum"], n_total)
+    worst = 0.0
+    for k in ("TAWSS", "OSI", "RRT", "ECAP", "TWSSG"):
+        a, b = np.asarray(fields[k]).ravel(), np.asarray(fin[k]).ravel()
+        ok = np.isfinite(a) & np.isfinite(b)
+        worst = max(worst, float(np.linalg.norm(a[ok] - b[ok]) / np.linalg.norm(b[ok])))
+    return worst
+
+
+# resident / end-to-end snapshot counts of the workloads a default run measures besides the headline one: >= 256
+# resident snapshots (full lanes in K2), end-to-end on as many whole host vectors as stay within ~10 GB of pinned memory
+OTHER_WORKLOADS = {"aneurysm_p1": (512, 512), "avf_p2": (256, 48), "vessel10m_p2": (256, 32)}
+
+
+def run_ours(args, rank: int, local_rank: int, world: int) -> None:
+    entry, ctx = measure(args.workload, args.snapshots, args.snapshots, args, rank, local_rank, world, True)
+    line = None
+    if rank == 0:
+        line = {"metric": METRIC, "value": entry["value"], "unit": UNIT, "n_gpus": world, "steps": entry["steps"],
+                "warmup": args.warmup, "ms_per_step": entry["ms_per_step"],
+                "ms_per_step_with_kernel_events": entry["ms_per_step_with_kernel_events"],
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": entry["config"], "clocks": entry["clocks"], "e2e": entry["e2e"],
+                "gpu_launches": entry["gpu_launches"], "roofline": entry["roofline"],
+                "cpu_baseline": entry["cpu_baseline"]}
+        if "parity_rel_l2" in entry:
+            line["parity_rel_l2"] = entry["parity_rel_l2"]
+    eng = ctx["eng"]
+    if rank == 0 and world == 1 and not args.no_io_leg:
         eng.close()
         try:
-            line["io"] = io_leg(wl, n_snap, u_host, local_rank)
+            wl = dict(ctx["g"], coef=ctx["coef"], dt=ctx["dt"], halo=ctx["halo"])
+            line["io"] = io_leg(wl, ctx["n_mine"], ctx["u_host"], local_rank, int(args.io_gib * (1 << 30)))
         except Exception as e:  # the headline line must not depend on the scratch file system
             line["io"] = {"error": f"{type(e).__name__}: {e}"}
-    print(json.dumps(line), flush=True)
+    eng.close()
+    del ctx, eng
+    if world == 1 and not args.no_other_workloads:
+        # BASELINE.json configs[2..4] ride in the same line (VERDICT r1: the driver's run must carry them)
+        line["other_workloads"] = []
+        import gc
+        for name, (n_res, n_e2e) in OTHER_WORKLOADS.items():
+            if name == args.workload:
+                continue
+            gc.collect()
+            try:
+                e, c = measure(name, n_res, n_e2e, args, rank, local_rank, world, False)
+                c["eng"].close()
+                del c
+                line["other_workloads"].append(e)
+            except Exception as ex:  # a workload that does not fit this box must not take the headline down
+                line["other_workloads"].append({"workload": name, "error": f"{type(ex).__name__}: {ex}"})
+    if rank == 0:
+        print(json.dumps(line), flush=True)
 
 
-def io_leg(wl, n_snap: int, u_host: np.ndarray, device: int):
+def io_leg(wl, n_snap: int, u_host: np.ndarray, device: int, io_bytes: int = 1 << 30):
     """HDF5 -> device, timed apart from the device-resident compute (north_star; SURVEY.md §8d "Timers").
 
     A `u.h5` in the layout create_hdf5.py:158-174 writes is produced from the same synthetic series (bounded to
@@ -403,7 +575,7 @@ def io_leg(wl, n_snap: int, u_host: np.ndarray, device: int):
     import io as _io
 
     order, vec_len = wl["order"], u_host.shape[1]
-    n_io = int(max(3, min(n_snap, (1 << 30) // (vec_len * 8))))
+    n_io = int(max(3, min(n_snap, io_bytes // (vec_len * 8))))
     tmp = Path(tempfile.mkdtemp(prefix="vasp_b200_io_"))
     try:
         (tmp / "Mesh").mkdir()
@@ -432,17 +604,18 @@ def io_leg(wl, n_snap: int, u_host: np.ndarray, device: int):
         eng = HemoEngine(device)
         eng.set_mesh(wl["xyz"], wl["tets"])
         eng.set_velocity_layout(order, refined_xyz=wl["points"] if order == 2 else None)
-        block = default_block_snapshots(vec_len)
+        block = default_block_snapshots(vec_len, eng.compact_len if eng.compaction_active else 0)
         eng.set_tuning(batch_snapshots=block, chunk_snapshots=0)
 
         def run_once():
             t0 = time.perf_counter()
             series = io_dolfin.VelocitySeries(path, "velocity", 1)
             eng.begin(MU, float(series.timestamps[1] - series.timestamps[0]))
-            reader = _BlockReader(series, 0, len(series), block)
+            reader = _BlockReader(series, 0, len(series), block, eng)
+            push = eng.push_compact if reader.compact else eng.push
             first = True
             for a, b, u in reader:
-                eng.push(u, flags=1 if first else 0)
+                push(u, flags=1 if first else 0)
                 first = False
             out = eng.finalize(len(series))
             dt_s = time.perf_counter() - t0
@@ -485,21 +658,15 @@ def io_leg(wl, n_snap: int, u_host: np.ndarray, device: int):
 
 def cpu_baseline(wl, n_snap: int):
     """Oracle C port on the host cores (bounded sample of the same workload), rank 0 at N = 1 only."""
-    from oracle import c_oracle, hemo_oracle as ho
-    node_of_p2 = None
-    if wl["order"] == 2:
-        p2 = ho.p2_node_coordinates(wl["xyz"], ho.p2_cell_nodes(wl["tets"])[1])
-        node_of_p2 = ho.match_points(p2, wl["points"], 1e-8 * float(np.ptp(wl["points"], axis=0).max()))
-    stress = ho.SurfaceStress(wl["xyz"], wl["tets"], MU, wl["order"], node_of_p2)
-    co = c_oracle.COracle(stress)
-    threads = c_oracle.max_threads()
+    stress, co, threads = oracle_for(wl)
     n = len(wl["points"])
     n_s = min(n_snap, max(threads, int(4.0e6 * threads / max(stress.nF, 1))))
+    n_s = max(2, min(n_s, int((4 << 30) // (3 * n * 8))))  # at most ~4 GB of host vectors
     u = synth.velocity_series(wl["basis"], wl["coef"][wl["halo"]:wl["halo"] + n_s])
     co.run(u[:max(1, n_s // 8)], wl["dt"], (0, n, 2 * n), threads=threads)  # warm-up
     reps, t_best = 0, float("inf")
     t_start = time.perf_counter()
-    while reps < 5 and time.perf_counter() - t_start < 20.0:
+    while reps < 5 and time.perf_counter() - t_start < (20.0 if n_s * stress.nF < 5e7 else 8.0):
         t0 = time.perf_counter()
         co.run(u, wl["dt"], (0, n, 2 * n), threads=threads)
         t_best = min(t_best, time.perf_counter() - t0)
@@ -519,6 +686,16 @@ def main() -> None:
     ap.add_argument("--snapshots", type=int, default=None, help="snapshots per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-io-leg", action="store_true", help="skip the HDF5 -> device and entry-point timings")
+    ap.add_argument("--io-gib", type=float, default=1.0, help="size bound of the u.h5 written for the HDF5 -> device leg")
+    ap.add_argument("--no-other-workloads", action="store_true",
+                    help="measure the headline workload only (default: BASELINE configs[2..4] ride in the same line)")
+    ap.add_argument("--other-steps", type=int, default=5, help="timed steps per non-headline workload")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak: every GPU processes --snapshots; strong: --snapshots are split over the GPUs")
+    ap.add_argument("--no-parity", dest="parity", action="store_false",
+                    help="N > 1: skip the comparison of the reduced fields with the restated reference")
+    ap.add_argument("--compaction", choices=["auto", "on", "off"], default="auto",
+                    help="wall-layer gather in front of the bus (default: the library's rule)")
     ap.add_argument("--wss", choices=["none", "steps", "matrix"], default="none",
                     help="device-resident pass also writes the per-snapshot WSS (default: the metric's indices only)")
     args = ap.parse_args()

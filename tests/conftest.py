@@ -12,6 +12,27 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """On a machine without a CUDA device a plain ``pytest`` skips the gpu-marked tests instead of failing in
+    ``vh_create``.  Where a device is visible nothing is skipped, and a missing library still fails loudly (no CPU
+    fallback exists); ``VASP_B200_STRICT_GPU=1`` turns the skipping off everywhere."""
+    import ctypes
+    import os
+    if os.environ.get("VASP_B200_STRICT_GPU") == "1":
+        return
+    try:
+        from vasp_b200 import _lib
+        n = ctypes.c_int(0)
+        if _lib.load().vh_device_count(ctypes.byref(n)) == 0 and n.value > 0:
+            return
+    except Exception:
+        return  # library missing or broken: let the tests say so
+    skip = pytest.mark.skip(reason="no CUDA device visible (set VASP_B200_STRICT_GPU=1 to fail instead)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def engine_lib():
     """The CUDA library; GPU tests fail loudly (not skip) if it is missing."""

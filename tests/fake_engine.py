@@ -14,10 +14,51 @@ PUSH_GLOBAL_FIRST, PUSH_HALO_FIRST = 1, 2
 
 
 class OracleHemoEngine:
+    #: tests flip this to exercise the entry point's compact route (rows gathered out of the file mapping); the gather
+    #: itself is the library's handle-free ``vh_host_gather`` -- data movement, no GPU needed
+    compact_route = False
+
     def __init__(self, device: int = 0):
         self.device = device
         self._S = None
         self._matrix = None
+
+    # ---- wall-layer compaction stand-ins (include/vasp_hemo.h)
+    @property
+    def compaction_active(self):
+        return bool(self.compact_route)
+
+    def _slots(self):
+        m = self._probe.maps
+        if self._order == 2:
+            cn = self._node[ho.p2_cell_nodes(self._tets)[0][m.wall_cells]]
+        else:
+            cn = self._node[ho.order_cells(self._tets)[m.wall_cells]]
+        return (np.unique(cn) * self._stride).astype(np.int32)
+
+    @property
+    def compact_len(self):
+        return 3 * ((len(self._slots()) + 31) // 32 * 32)
+
+    def compact_rows(self, addresses, out):
+        import ctypes
+        from vasp_b200 import _lib
+        sl = self._slots()
+        nwp = self.compact_len // 3
+        slp = np.concatenate([sl, np.full(nwp - len(sl), sl[-1], np.int32)])
+        addresses = np.ascontiguousarray(addresses, dtype=np.uint64)
+        off = (ctypes.c_int64 * 3)(*self._off)
+        assert _lib.load().vh_host_gather(addresses.ctypes.data, None, 0, len(addresses), slp.ctypes.data, nwp, off,
+                                          out.ctypes.data, out.strides[0], 2) == 0
+        return out
+
+    def push_compact(self, c, flags=0, wss_out=None):
+        sl, nwp = self._slots().astype(np.int64), self.compact_len // 3
+        top = max(self._off) + int(sl.max()) + 1
+        u = np.full((len(c), top), np.nan)  # anything outside the wall layer must never be read
+        for k, o in enumerate(self._off):
+            u[:, o + sl] = np.asarray(c)[:, k * nwp:k * nwp + len(sl)]
+        return self.push(u, flags=flags, wss_out=wss_out)
 
     # ---- K0 stand-ins
     def set_mesh(self, xyz, tets):

@@ -123,3 +123,42 @@ def test_p1_extension_reads_vertex_data(cpu_engine, tmp_path):
     for name in H.FIELDS:
         got = io_dolfin.read_checkpoint(tmp_path / "Hemodynamic_indices", name, 0)["values"]
         assert H.rel_l2(got, fin[name]) < 1e-12, name
+
+
+@pytest.mark.parametrize("route", ["u_h5", "raw"])
+def test_compact_route_reads_only_the_wall_layer_out_of_the_file_mapping(cpu_engine, tmp_path, monkeypatch, route):
+    """With wall-layer compaction active the block reader never copies a snapshot whole: the engine gathers the
+    wall-layer dofs straight out of the read-only mapping of ``u.h5`` (or of the raw turtleFSI arrays) and the entry
+    point pushes compact rows.  Output files must equal those of the whole-vector route byte for byte; the stand-in
+    poisons everything outside the wall layer, so a dof that should not matter cannot leak in."""
+    folders = {}
+    for mode in (False, True):
+        monkeypatch.setattr(OracleHemoEngine, "compact_route", mode)
+        d = tmp_path / f"run{int(mode)}"
+        d.mkdir()
+        if route == "raw":
+            H.write_turtle_folder(d, _u_syn(6), n_snap=7, dt=0.01, mu=3.5e-3, save_step=2, split_at=3)
+        else:
+            _make_folder(d, _u_syn(6), 7, 0.05, 3.5e-3)
+        ch.main(["--folder", str(d)])
+        folders[mode] = d / "Hemodynamic_indices"
+    for name in ch.INDEX_NAMES:
+        assert (folders[True] / f"{name}.h5").read_bytes() == (folders[False] / f"{name}.h5").read_bytes(), name
+
+
+def test_block_reader_in_compact_mode_handles_ragged_blocks(cpu_engine, tmp_path, monkeypatch):
+    monkeypatch.setattr(OracleHemoEngine, "compact_route", True)
+    xyz, tets, rx, vecs, times = _make_folder(tmp_path, _u_syn(8), 8, 0.05, 3.5e-3)
+    series = io_dolfin.VelocitySeries(tmp_path / "Visualization_separate_domain" / "u.h5", "velocity", 1)
+    eng = OracleHemoEngine()
+    eng.set_mesh(xyz, tets)
+    _, rt = io_dolfin.read_mesh(tmp_path / "Mesh" / "mesh_refined_fluid.h5")
+    comp_offset, node_stride, perm = series.layout(rt, len(rx))
+    eng.set_velocity_layout(2, refined_xyz=rx, node_perm=perm, comp_offset=comp_offset, node_stride=node_stride)
+    reader = ch._BlockReader(series, 1, 8, 3, eng)          # snapshots 1..7 in blocks of 3, 4 (no single trailing one)
+    assert reader.compact and reader.ranges == [(1, 4), (4, 8)] and reader.max_rows == 4
+    sl, nwp, n = eng._slots().astype(np.int64), eng.compact_len // 3, len(rx)
+    for a, b, c in reader:
+        for k in range(3):
+            assert np.array_equal(c[:, k * nwp:k * nwp + len(sl)], vecs[a:b, k * n + sl])
+    series.close()

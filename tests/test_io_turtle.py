@@ -23,8 +23,12 @@ def test_step_selection_matches_the_reference_tests():
         io_turtle.select_steps(times, 0.001, start_time=0.002, end_time=0.001)
     with pytest.raises(AssertionError):
         io_turtle.select_steps(times, 0.001, end_time=0.004)
-    with pytest.raises(ValueError):              # would index from the end of the list in the reference
-        io_turtle.select_steps([0.0, 0.001], 0.001)
+    # first saved time just below save_time_step: int(t0 / dt) - 1 = -1, and the reference's range(-1, last) indexes
+    # its lists from the END for that first step (create_hdf5.py:128-131); same selection here
+    assert io_turtle.select_steps([0.0, 0.001], 0.001) == [1, 0]
+    assert io_turtle.select_steps([0.00099999, 0.002, 0.003], 0.001) == [2, 0, 1, 2]
+    with pytest.raises(ValueError):              # IndexError in the reference
+        io_turtle.select_steps([0.001, 0.002], 0.001, end_time=0.002, start_time=-0.005)
 
 
 def test_raw_series_is_the_slice_create_hdf5_would_write(tmp_path):

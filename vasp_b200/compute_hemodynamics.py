@@ -123,18 +123,31 @@ class _Drain:
         self._check()
 
 
-def default_block_snapshots(vec_len: int) -> int:
+def default_block_snapshots(vec_len: int, compact_len: int = 0) -> int:
     """Snapshots per pinned read buffer: ~16 MiB, at least 2 and at most 512.  Small blocks matter twice: nothing
     overlaps the first block's read, and pinning memory costs about as much per byte as reading it (measured:
-    2 x 260 MB buffers cost more than reading the 1 GB file from the page cache, profiles/r1io_*)."""
-    return int(min(512, max(2, (16 << 20) // (vec_len * 8))))
+    2 x 260 MB buffers cost more than reading the 1 GB file from the page cache, profiles/r1io_*).  When the wall layer
+    is gathered on the way (``compact_len`` doubles per snapshot land in the buffer instead of ``vec_len``) the rows
+    are small, and a block should also fill the lanes of the traction kernel: up to 64 snapshots within 1 GiB."""
+    row = (compact_len or vec_len) * 8
+    n = (16 << 20) // row
+    if compact_len:
+        n = max(n, min(64, (1 << 30) // row))
+    return int(min(512, max(2, n)))
 
 
 class _BlockReader:
-    """Reads snapshot blocks of ``u.h5`` into two pinned buffers, one block ahead of the consumer."""
+    """Reads snapshot blocks of ``u.h5`` into two pinned buffers, one block ahead of the consumer.
 
-    def __init__(self, series: io_dolfin.VelocitySeries, first: int, last: int, block: int):
+    With an ``engine`` whose wall-layer compaction is active the blocks hold COMPACT rows: the engine's thread pool
+    gathers the wall-layer dofs straight out of the read-only mapping of the file (the page cache), so a snapshot is
+    never copied whole and only ``24 * n_wall_nodes`` bytes per snapshot cross the bus (``compact`` is then True and
+    the consumer pushes with ``push_compact``)."""
+
+    def __init__(self, series, first: int, last: int, block: int, engine=None):
         self.series, self.block = series, max(2, block)
+        self.compact = bool(engine is not None and engine.compaction_active and hasattr(series, "row_addresses"))
+        self._engine = engine
         self.ranges = []
         pos = first
         while pos < last:
@@ -143,12 +156,16 @@ class _BlockReader:
                 end = last
             self.ranges.append((pos, end))
             pos = end
-        rows = max((b - a for a, b in self.ranges), default=1)
-        self.bufs = [pinned_empty((rows, series.vec_len)) for _ in range(2)]
+        self.max_rows = rows = max((b - a for a, b in self.ranges), default=1)
+        if self.compact:
+            self._addr = series.row_addresses()
+            self.bufs = [pinned_empty((rows, engine.compact_len)) for _ in range(2)]
+        else:
+            self.bufs = [pinned_empty((rows, series.vec_len)) for _ in range(2)]
         self.io_seconds = 0.0
         # page cache -> pinned memory is a memcpy per pread: one thread moves ~7 GB/s, the PCIe link takes 52
         n_threads = int(os.environ.get("VASP_B200_READ_THREADS", min(4, os.cpu_count() or 1)))
-        self._pool = ThreadPoolExecutor(n_threads) if n_threads > 1 else None
+        self._pool = ThreadPoolExecutor(n_threads) if n_threads > 1 and not self.compact else None
         self._ready = [threading.Event(), threading.Event()]
         self._free = [threading.Event(), threading.Event()]
         for e in self._free:
@@ -157,6 +174,14 @@ class _BlockReader:
         self._thread = threading.Thread(target=self._run, daemon=True)
         self._thread.start()
 
+    def _read(self, buf, a: int, b: int, nxt) -> None:
+        if self.compact:
+            if nxt is not None:
+                self.series.advise(*nxt)  # the kernel reads ahead while this block is gathered
+            self._engine.compact_rows(self._addr[a:b], buf)
+        else:
+            self.series.read_into(buf, a, b, self._pool)
+
     def _run(self) -> None:
         try:
             for i, (a, b) in enumerate(self.ranges):
@@ -164,7 +189,7 @@ class _BlockReader:
                 self._free[slot].wait()
                 self._free[slot].clear()
                 t0 = time.perf_counter()
-                self.series.read_into(self.bufs[slot], a, b, self._pool)
+                self._read(self.bufs[slot], a, b, self.ranges[i + 1] if i + 1 < len(self.ranges) else None)
                 self.io_seconds += time.perf_counter() - t0
                 self._ready[slot].set()
         except BaseException as e:  # surfaced in the consumer
@@ -254,8 +279,9 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
 
     shard = plan_shard(n_snap, rank, world)
     nF = eng.nF
+    compacting = eng.compaction_active and hasattr(series, "row_addresses")
     if block_snapshots is None:
-        block_snapshots = default_block_snapshots(series.vec_len)
+        block_snapshots = default_block_snapshots(series.vec_len, eng.compact_len if compacting else 0)
         if wss_matrix_folder is not None:
             # the matrix comes back as a pitched copy of 9 nF rows of (block x 8) bytes: keep the rows >= 256 bytes
             # unless that would pin more than 1 GiB per read buffer
@@ -269,6 +295,7 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
     elif shard.count:
         shard_file = np.lib.format.open_memmap(hemodynamic_indices_path / f".WSS_shard{rank}.npy", mode="w+",
                                                dtype=np.float64, shape=(shard.count, nF, 3, 3))
+    reader = _BlockReader(series, shard.read_start, shard.stop, block_snapshots, eng)
     direct = None
     if wss_matrix_folder is not None:
         assert world == 1, "wss_matrix_folder: the direct WSS matrix is assembled by a single rank"
@@ -278,9 +305,8 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
         direct.attach()
         wss_buf = None
     else:
-        wss_buf = pinned_empty((block_snapshots + 1, nF, 3, 3))
+        wss_buf = pinned_empty((reader.max_rows, nF, 3, 3))  # the reader may merge a trailing snapshot into a block
 
-    reader = _BlockReader(series, shard.read_start, shard.stop, block_snapshots)
     first, done = True, 0
     t_setup = time.perf_counter() - t_begin
     t_push = 0.0
@@ -306,11 +332,12 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
         slot = i & 1
         drain.wait_free(slot)  # the block written two pushes ago has left this buffer
         t0 = time.perf_counter()
+        push = eng.push_compact if reader.compact else eng.push
         if direct is not None:
-            m = eng.push(u, flags=flags)  # columns [done, done + n_real) of the time-major matrix
+            m = push(u, flags=flags)  # columns [done, done + n_real) of the time-major matrix
             out_block = np.ascontiguousarray(m[:, done:done + n_real].T).reshape(n_real, nF, 3, 3)
         else:
-            eng.push(u, flags=flags, wss_out=wss_bufs[slot])
+            push(u, flags=flags, wss_out=wss_bufs[slot])
             out_block = wss_bufs[slot]
         t_push += time.perf_counter() - t0
         drain.submit(slot, out_block, done, n_real)

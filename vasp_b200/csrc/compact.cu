@@ -164,12 +164,17 @@ void gather_range(const double* __restrict__ src, const int32_t* __restrict__ sl
 bool compact_wanted(const vh_handle* h) {
     if (h->compact_mode == 1) return false;
     if (h->compact_mode == 2) return true;
-    // auto: the gather costs host memory bandwidth on the lines it touches, the copy costs PCIe time on every byte;
-    // below about a third of the slots the gather wins (measured)
-    static const double limit = [] {
+    // auto.  Measured on the GPU box (profiles/r2_bus_variants.md): the gather streams the vector through the host
+    // cores at ~10 GB/s per thread up to ~160 GB/s (it touches nearly every cache line once the wall layer is more than
+    // a few per cent of the nodes), the plain copy moves every byte at 54 GB/s over PCIe.  With >= 6 threads the
+    // gather wins up to a wall-layer share of about a third (1.5x at 20 %, 2.7x at 7 %); at 72 % (the tutorial-size
+    // mesh) it loses.  With fewer threads only a very thin wall layer pays.
+    static const double limit_env = [] {
         const char* e = getenv("VASP_B200_COMPACT_RATIO");
-        return e && *e ? atof(e) : 0.35;
+        return e && *e ? atof(e) : -1.0;
     }();
+    const int threads = h->host_threads > 0 ? h->host_threads : auto_threads();
+    const double limit = limit_env >= 0.0 ? limit_env : (threads >= 6 ? 0.35 : 0.05);
     const double slots = (double)((h->vec_len + 2) / 3);
     return slots > 0 && (double)h->nWn_pad <= limit * slots;
 }

@@ -168,9 +168,32 @@ class VelocitySeries:
             list(pool.map(self.pread_chunk, jobs))
         return out
 
+    def row_addresses(self) -> np.ndarray:
+        """Host address of every selected vector inside the read-only ``mmap`` of the file (``uint64``): the
+        wall-layer gather of the engine (``HemoEngine.compact_rows``) reads the page cache in place."""
+        if getattr(self, "_base", None) is None:
+            self._view = np.frombuffer(self._f._buf, dtype=np.uint8)
+            self._base = int(self._view.ctypes.data)
+        return (np.uint64(self._base) + self.offsets.astype(np.uint64)).astype(np.uint64)
+
+    def advise(self, first: int, last: int) -> None:
+        """Tell the kernel that snapshots ``[first, last)`` are about to be read through the mapping."""
+        if last <= first:
+            return
+        try:
+            import mmap as _mmap
+            page = _mmap.PAGESIZE
+            lo = int(self.offsets[first]) // page * page
+            hi = int(self.offsets[last - 1]) + self.vec_len * 8
+            self._f._buf.madvise(_mmap.MADV_WILLNEED, lo, hi - lo)
+        except (AttributeError, OSError, ValueError):
+            pass
+
     def close(self) -> None:
         self._ds = []
         self._g = None
+        self._view = None
+        self._base = None
         self._f.close()
 
 

@@ -19,6 +19,7 @@ What is reproduced from the reference, line by line:
 """
 from __future__ import annotations
 
+import logging
 import os
 import re
 from pathlib import Path
@@ -76,11 +77,17 @@ def select_steps(timevalues: Sequence[float], save_time_step: float, stride: int
     end_time = end_time if end_time is not None else timevalues[-1]
     first = int(start_time / save_time_step) - 1
     last = int(end_time / save_time_step)
-    if first < 0 or last > len(timevalues):
-        # the reference would index from the END of the list (first < 0) or run off it; neither is a usable series
-        raise ValueError(f"start/end time select steps [{first}, {last}) outside the {len(timevalues)} saved steps "
+    n = len(timevalues)
+    if first < -n or last > n:
+        # the reference would raise IndexError on timevalue_list[file_counter]
+        raise ValueError(f"start/end time select steps [{first}, {last}) outside the {n} saved steps "
                          f"(save_time_step = {save_time_step})")
-    return list(range(first, last, stride))
+    if first < 0:
+        # int(start / save_time_step) - 1 < 0 happens when the first saved time is an accumulated float just below
+        # save_time_step.  The reference then indexes its lists with a negative file_counter, i.e. from the END
+        # (create_hdf5.py:128-131): same steps here, with a warning, so that both tools accept the same runs.
+        logging.warning(f"WARNING : start index {first} is negative; like the reference, counting from the last step")
+    return [i if i >= 0 else n + i for i in range(first, last, stride)]
 
 
 class TurtleVelocitySeries:
@@ -170,7 +177,20 @@ class TurtleVelocitySeries:
             list(pool.map(run, jobs))
         return out
 
+    def row_addresses(self) -> np.ndarray:
+        """Host address of every selected raw array inside the read-only ``mmap`` of its file (see
+        :meth:`io_dolfin.VelocitySeries.row_addresses`)."""
+        if not getattr(self, "_views", None):
+            self._views = {fd: np.frombuffer(f._buf, dtype=np.uint8) for f in self._files.values()
+                           for fd in [f._fh.fileno()]}
+        base = np.array([self._views[fd].ctypes.data for fd in self._fd], dtype=np.uint64)
+        return base + self.offsets.astype(np.uint64)
+
+    def advise(self, first: int, last: int) -> None:
+        pass  # several files: left to the kernel's read-ahead
+
     def close(self) -> None:
+        self._views = None
         for f in self._files.values():
             f.close()
         self._files = {}
