@@ -55,6 +55,21 @@ assert c2 == n_snap
 for name in H.FIELDS:
     assert H.rel_l2(out2[name], fin[name]) < 1e-10, name
 assert abs(comm.max(float(rank)) - (world - 1)) == 0
+# back-to-back loops with the results left on the device: the fused reduction of loop s runs on its own stream while
+# K1/K2 of loop s + 1 are already working (the bench's resident step); every loop scales the input, so a reduction
+# that read a half of the sum block too late or too early would show in the last loop's sums
+d = eng.device_alloc(case["u"].nbytes)
+eng.h2d(d, case["u"])
+row = case["u"].strides[0]
+lo = shard.read_start
+for rep in range(6):
+    eng.begin(mu * (rep + 1), case["dt"])
+    eng.push_device(d + lo * row, shard.stop - lo, row, shard.first_push_flags())
+    comm.reduce_finalize(n_snap, host=False)
+s3, c3 = eng.sums()
+assert c3 == n_snap
+assert H.rel_l2(s3[:9].reshape(3, 3, -1).transpose(2, 0, 1), 6 * res["wss_sum"]) < 1e-10
+eng.device_free(d)
 comm.barrier()
 eng.close()
 print("ok", rank)

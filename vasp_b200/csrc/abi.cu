@@ -79,12 +79,14 @@ int ensure_run_buffers(vh_handle* h) {
         VH_CUDA(cudaMalloc(&h->d_tau_last[0], sizeof(double) * 9 * nF));
         VH_CUDA(cudaMalloc(&h->d_tau_last[1], sizeof(double) * 9 * nF));
         VH_CUDA(cudaMalloc(&h->d_out5, sizeof(double) * 15 * nF));
+        VH_CUDA(cudaMalloc(&h->d_out5_peer, sizeof(double) * 15 * nF));
     }
     return VH_OK;
 }
 
 // the running sums are zeroed lazily (see vh_begin); anyone who reads them before the first push calls this
 int settle_sums(vh_handle* h) {
+    vh_join_peer(h);
     if (h->sums_pending_zero) {
         VH_CUDA(cudaMemsetAsync(h->d_sums, 0, sizeof(double) * (VH_NSUM * h->nF + 1), h->s_compute));
         h->sums_pending_zero = false;
@@ -339,14 +341,15 @@ int vh_set_wss_layout(vh_handle* h, int64_t ld, int64_t col0) {
 
 // D2H of the five result fields: one copy into a pinned staging buffer (user arrays are usually pageable numpy
 // memory, where every cudaMemcpyAsync degenerates into a staged synchronous copy), then host memcpy
-static int export_out5(vh_handle* h, double* const outs[5]) {
+static int export_out5(vh_handle* h, double* const outs[5], const double* d_src = nullptr, cudaStream_t st = nullptr) {
     const int64_t n3 = 3 * h->nF;
     bool any = false;
     for (int i = 0; i < 5; ++i) any = any || outs[i];
     if (!any) return VH_OK;  // results stay in HBM, the call stays asynchronous
+    if (!st) st = h->s_compute;
     if (!h->h_out5) VH_CUDA(cudaHostAlloc((void**)&h->h_out5, sizeof(double) * 5 * n3, cudaHostAllocDefault));
-    VH_CUDA(cudaMemcpyAsync(h->h_out5, h->d_out5, sizeof(double) * 5 * n3, cudaMemcpyDeviceToHost, h->s_compute));
-    VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    VH_CUDA(cudaMemcpyAsync(h->h_out5, d_src ? d_src : h->d_out5, sizeof(double) * 5 * n3, cudaMemcpyDeviceToHost, st));
+    VH_CUDA(cudaStreamSynchronize(st));
     for (int i = 0; i < 5; ++i)
         if (outs[i]) memcpy(outs[i], h->h_out5 + i * n3, sizeof(double) * n3);
     return VH_OK;
@@ -657,6 +660,7 @@ int vh_get_sums(vh_handle* h, double* sums, int64_t* count) {
     VH_TRY(check_ready(h, "vh_get_sums"));
     VH_TRY(settle_sums(h));
     VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    VH_CUDA(cudaStreamSynchronize(h->s_aux));
     const double* src = h->sums_reduced ? h->d_sums_red : h->d_sums;  // after a fused peer reduction: the global sums
     if (sums) VH_CUDA(cudaMemcpy(sums, src, sizeof(double) * VH_NSUM * h->nF, cudaMemcpyDeviceToHost));
     if (h->count_on_device) {  // left there by the all-reduce / peer reduction, which do not synchronise
@@ -675,6 +679,7 @@ int vh_set_sums(vh_handle* h, const double* sums, int64_t count) {
     h->sums_pending_zero = false;
     h->sums_reduced = false;
     h->out5_count = -1;
+    vh_join_peer(h);
     VH_CUDA(cudaStreamSynchronize(h->s_compute));
     VH_CUDA(cudaMemcpy(h->d_sums, sums, sizeof(double) * VH_NSUM * h->nF, cudaMemcpyHostToDevice));
     h->count = count;
@@ -716,6 +721,7 @@ int vh_finalize(vh_handle* h, int64_t n_total, double* tawss, double* osi, doubl
 // after one looks at it, so a lost rank ends in an error on the survivors instead of a hung GPU.
 static int peer_check(vh_handle* h) {
     if (!h->peer_unchecked) return VH_OK;
+    VH_CUDA(cudaStreamSynchronize(h->s_aux));
     uint64_t lost = 0;
     VH_CUDA(cudaMemcpyAsync(&lost, h->d_sums_block + 2 * h->sum_stride + VH_MAX_PEERS, sizeof(lost),
                             cudaMemcpyDeviceToHost, h->s_compute));
@@ -732,6 +738,7 @@ int vh_sync(vh_handle* h) {
     VH_CUDA(cudaSetDevice(h->device));
     VH_CUDA(cudaStreamSynchronize(h->s_copy));
     VH_CUDA(cudaStreamSynchronize(h->s_compute));
+    VH_CUDA(cudaStreamSynchronize(h->s_aux));
     return peer_check(h);
 }
 
@@ -784,6 +791,8 @@ int vh_timer_start(vh_handle* h) {
 int vh_timer_stop(vh_handle* h, double* ms) {
     VH_CHECK(h && ms, VH_ERR_ARG, "vh_timer_stop: null argument");
     VH_CUDA(cudaSetDevice(h->device));
+    if (h->peer_pending) VH_CUDA(cudaStreamWaitEvent(h->s_compute, h->ev_join, 0));  // the timed region ends with the
+                                                                                       // last cross-GPU reduction
     VH_CUDA(cudaEventRecord(h->ev_t1, h->s_compute));
     VH_CUDA(cudaEventSynchronize(h->ev_t1));
     float f = 0.f;
@@ -890,7 +899,7 @@ int vh_nccl_init(vh_handle* h, const char id[128], int rank, int world) {
 int vh_nccl_allreduce_sums(vh_handle* h) {
     VH_TRY(check_ready(h, "vh_nccl_allreduce_sums"));
     VH_CHECK(h->nccl_comm, VH_ERR_NCCL, "vh_nccl_allreduce_sums: call vh_nccl_init first");
-    VH_TRY(settle_sums(h));
+    VH_TRY(settle_sums(h));  // also orders s_compute behind a fused reduction still in flight
     // one collective, stream-ordered, no host synchronisation: the snapshot count rides behind the 15 * nF sums
     const int64_t n = VH_NSUM * h->nF;
     if (!h->count_on_device) {
@@ -1010,13 +1019,12 @@ int vh_peer_reduce_finalize(vh_handle* h, int64_t n_total, double* tawss, double
     for (int q = 0; q < VH_MAX_PEERS; ++q) pb.block[q] = h->peer_block[q];
     const int64_t half_off = (int64_t)h->loop_parity * h->sum_stride, flags_off = 2 * h->sum_stride;
     h->peer_epoch += 1;
-    VH_TRY(k4_peer_reduce_finalize(h, pb, half_off, flags_off, h->peer_epoch, n_total, h->d_sums_red, h->d_out5));
+    VH_TRY(k4_peer_reduce_finalize(h, pb, half_off, flags_off, h->peer_epoch, n_total, h->d_sums_red, h->d_out5_peer));
     h->sums_reduced = true;
     h->count_on_device = true;
-    h->out5_count = -1;  // d_out5 holds the global indices; the local count no longer describes it
     h->peer_unchecked = true;
     double* const outs[5] = {tawss, osi, rrt, ecap, twssg};
-    VH_TRY(export_out5(h, outs));
+    VH_TRY(export_out5(h, outs, h->d_out5_peer, h->s_aux));
     if (tawss || osi || rrt || ecap || twssg) return peer_check(h);  // export_out5 synchronised
     return VH_OK;
 }

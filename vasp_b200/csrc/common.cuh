@@ -83,7 +83,7 @@ struct FacetTables {
 struct vh_handle {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_aux = nullptr;  // s_aux: multi-facet-cell K2 launch
+    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_aux = nullptr;  // s_aux: the fused cross-GPU reduction
     cudaStream_t s_d2h = nullptr;  // WSS blocks back to the host: its own stream, so that the next H2D does not queue behind it
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
@@ -151,8 +151,12 @@ struct vh_handle {
     // programmatic stream serialization per kernel: bit 0 K1, bit 1 K2, bit 2 K3 (VASP_B200_PDL).  Measured (profiles/
     // r1pdl): K1 + K2 is the best mask (55.8 us per headline step against 64 without); adding K3 costs 30 us on P2.
     int pdl = 11;                  // bit 3: the fused peer reduction after K3 (2 GPUs, headline: 72.4 -> 70.3 us per step)
-    bool k2_configured[2] = {false, false};  // cudaFuncSetAttribute done on this handle's device (P1, P2)
+    bool k2_configured[8] = {false, false, false, false, false, false, false, false};  // cudaFuncSetAttribute done on this handle's device, per (order, launch shape)
     bool peer_unchecked = false;   // a fused reduction was enqueued and its "peer lost" word not looked at yet
+    // The fused reduction runs on s_aux behind the K3 of its time loop, so the next loop's K1/K2 overlap the cross-GPU
+    // wait; whoever next WRITES the running sums on s_compute first waits for it (ev_join) -- see vh_join_peer.
+    bool peer_pending = false;
+    double* d_out5_peer = nullptr; // [5][3*nF] global indices written by the fused reduction (K3 keeps writing d_out5)
     double* peer_block[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double* d_tau_last[2] = {nullptr, nullptr};  // [9][nF], ping-pong (read by first chunk, written by last)
     int tau_cur = 0;
@@ -217,6 +221,8 @@ struct PeerBlocks {
 int k4_peer_reduce_finalize(vh_handle* h, const PeerBlocks& pb, int64_t half_off, int64_t flags_off, uint64_t epoch,
                             int64_t n_total, double* d_red, double* d_out5);
 int k_free_run_buffers(vh_handle* h);
+// s_compute waits for a fused peer reduction still in flight on s_aux (before anything overwrites the running sums)
+void vh_join_peer(vh_handle* h);
 
 FacetTables vh_tables(const vh_handle* h);
 

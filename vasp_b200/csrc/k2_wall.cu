@@ -45,6 +45,7 @@ constexpr double Q_C = 0.47014206410511505, Q_D = 0.05971587178976981;
 constexpr double Q_W0 = 0.225, Q_W1 = 0.12593918054482717, Q_W2 = 0.13239415278850616;
 
 constexpr int K2_WARPS = 4;
+constexpr int K2_OCC_P1 = 3, K2_OCC_P2 = 3;  // default launch shape per order (K2Launch)
 
 // Three code paths share one launch (k2_wall<ORDER>):
 //   k2_body_flat2     P1 data, cell with one exterior facet: values by ld.global.nc straight into registers (register
@@ -60,12 +61,20 @@ constexpr int K2_WARPS = 4;
 // effect: W is L2-resident after K1); a TMA bulk copy per row (bypasses L1, where neighbouring facets share rows).
 // Shared memory per warp, in doubles.
 constexpr int K2_P2_STAGE = 30 * 32;                 // one tile of the 30 dof components
-constexpr int K2_P2_WARP = 2 * K2_P2_STAGE + 10;    // two stages + tau of the last lane of the previous pass
-template <int ORDER>
+// Launch shapes (template parameter OCC = resident blocks per SM the kernel is compiled for):
+//   OCC 3  168 registers, 12 warps per SM; P2 landing buffer of two tiles, P1 register double buffer      (round 1)
+//   OCC 4  128 registers, 16 warps per SM; P2 landing buffer of ONE tile that is refilled as soon as the traction of
+//          the current tile has been formed (the time reductions -- 45 % of a pass -- cover the copy); P1 loads its
+//          pass at the top of the loop and leaves the latency to the other warps
+template <int ORDER, int OCC>
 struct K2Launch {
     static constexpr int NV = ORDER == 2 ? 30 : 12;
+    static constexpr bool DIRECT = OCC == 6;      // P2 values by direct loads (k2_body_p2_direct), 3 blocks per SM
+    static constexpr int BLOCKS = DIRECT ? 3 : OCC;
+    static constexpr int STAGES = DIRECT ? 0 : OCC >= 4 ? 1 : 2;
+    static constexpr int P2_WARP = STAGES * K2_P2_STAGE + 10;  // landing stages + tau of the last lane of the previous pass
     static constexpr int MULTI_WARP = NV * VH_MROW + 10;  // operator + carry
-    static constexpr int WARP_DOUBLES = ORDER == 2 ? (K2_P2_WARP > MULTI_WARP ? K2_P2_WARP : MULTI_WARP) : MULTI_WARP;
+    static constexpr int WARP_DOUBLES = ORDER == 2 ? (P2_WARP > MULTI_WARP ? P2_WARP : MULTI_WARP) : MULTI_WARP;
     static constexpr int SMEM_BYTES = K2_WARPS * WARP_DOUBLES * (int)sizeof(double);
 };
 
@@ -254,7 +263,9 @@ __device__ __forceinline__ void hemo_indices(const double (&v)[5], double count,
 
 // One warp = one facet x one time segment; the 32 lanes are the 32 columns of a tile of the staged block.
 // P2 data, facets whose cell owns no other exterior facet (work[0, multi_start)).
+template <int OCC>
 __device__ __forceinline__ void k2_body_p2(const K2Args& a, const K2Seg& sg, int bx, int y, double* k2_smem) {
+    using L = K2Launch<2, OCC>;
     const FacetTables& T = a.T;
     const int64_t nF = T.nF;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -265,16 +276,16 @@ __device__ __forceinline__ void k2_body_p2(const K2Args& a, const K2Seg& sg, int
     const int t0 = y * sg.tile_base + min(y, sg.tile_extra);
     const int nt = sg.tile_base + (y < sg.tile_extra ? 1 : 0);
 
-    double* const ring = k2_smem + (size_t)wib * K2Launch<2>::WARP_DOUBLES;
-    double* const carry_s = ring + 2 * K2_P2_STAGE;
+    double* const ring = k2_smem + (size_t)wib * L::WARP_DOUBLES;
+    double* const carry_s = ring + L::STAGES * K2_P2_STAGE;
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring + lane);
 
     // element offset inside W of (cell dof k, tile t0, component 0, this lane's column); W holds < 2^31 doubles
     int32_t rb[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) rb[k] = (T.row[(int64_t)k * nF + f] * a.ntile_ld + t0) * 96 + lane;
-    auto fetch = [&](int j) {  // tile t0 + j -> landing stage j & 1
-        const uint32_t dst = ring_s + (uint32_t)((j & 1) * K2_P2_STAGE * sizeof(double));
+    auto fetch = [&](int j) {  // tile t0 + j -> landing stage j % STAGES
+        const uint32_t dst = ring_s + (uint32_t)((j % L::STAGES) * K2_P2_STAGE * sizeof(double));
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
             const double* p = a.W + (rb[k] + j * 96);
@@ -306,15 +317,18 @@ __device__ __forceinline__ void k2_body_p2(const K2Args& a, const K2Seg& sg, int
     for (int i = 0; i < VH_NSUM; ++i) acc[i] = 0.0;
 
     for (int j = 0; j < nt; ++j) {
-        if (j + 1 < nt) {
+        if (L::STAGES == 2 && j + 1 < nt) {
             fetch(j + 1);
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
-        const double* sv = ring + (j & 1) * K2_P2_STAGE + lane;  // sv[(3 k + d) * 32]
+        const double* sv = ring + (j % L::STAGES) * K2_P2_STAGE + lane;  // sv[(3 k + d) * 32]
         double tau[9], dw[9];
         tau_p2([&](int i) { return gr[i]; }, [&](int q) { return sv[q * 32]; }, a.mu, tau);
+        // one landing stage: every value of this tile has been read (each lane reads and refills only its own column,
+        // and the asm memory clobber keeps the reads above the copy), so the next tile can start to arrive now
+        if (L::STAGES == 1 && j + 1 < nt) fetch(j + 1);
         const int col = (t0 + j) * 32 + lane;
         const bool live = col >= a.r0 && col < a.ncol;
         // w = tau - tau_prev (the 1 / dt is applied to the sums at the end: |.| and P are homogeneous)
@@ -348,11 +362,89 @@ __device__ __forceinline__ void k2_body_p2(const K2Args& a, const K2Seg& sg, int
     store_partials(acc, sg.part + (int64_t)y * VH_NSUM * T.n_work + w, T.n_work, a.inv_dt, lane);
 }
 
+// P2 data, cell with one exterior facet, values straight from global memory into registers (ld.global.nc.f64, no
+// shared-memory landing buffer): 30 loads per pass instead of 30 cp.async + 30 LDS, i.e. a third of the wavefronts on
+// the L1/shared-memory data path.  No prefetch across passes (60 registers per tile would not fit twice): the other
+// resident warps cover the latency.
+__device__ __forceinline__ void k2_body_p2_direct(const K2Args& a, const K2Seg& sg, int bx, int y, double* k2_smem,
+                                                  int warp_doubles) {
+    const FacetTables& T = a.T;
+    const int64_t nF = T.nF;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t w = (int64_t)bx * K2_WARPS + wib;
+    if (w >= T.multi_start) return;
+    const int32_t f = T.work[w];
+    if (f < 0) return;  // padding entry (warp-uniform)
+    const int t0 = y * sg.tile_base + min(y, sg.tile_extra);
+    const int nt = sg.tile_base + (y < sg.tile_extra ? 1 : 0);
+    double* const carry_s = k2_smem + (size_t)wib * warp_doubles;  // tau of the last lane of the previous pass
+
+    int32_t rb[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) rb[k] = (T.row[(int64_t)k * nF + f] * a.ntile_ld + t0) * 96 + lane;
+    double gr[19];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) gr[i] = T.glam[(int64_t)i * nF + f];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) gr[12 + d] = T.normal[(int64_t)d * nF + f];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) gr[15 + b] = gr[3 * b] * gr[12] + gr[3 * b + 1] * gr[13] + gr[3 * b + 2] * gr[14];
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) carry_s[i] = (y == 0 && a.prev_mode == 1) ? a.tau_last_in[(int64_t)i * nF + f] : 0.0;
+    }
+    __syncwarp();
+
+    double acc[VH_NSUM];
+#pragma unroll
+    for (int i = 0; i < VH_NSUM; ++i) acc[i] = 0.0;
+
+    for (int j = 0; j < nt; ++j) {
+        double u[30];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            const double* p = a.W + (rb[k] + j * 96);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) u[3 * k + d] = __ldg(p + 32 * d);
+        }
+        double tau[9], dw[9];
+        tau_p2([&](int i) { return gr[i]; }, [&](int q) { return u[q]; }, a.mu, tau);
+        const int col = (t0 + j) * 32 + lane;
+        const bool live = col >= a.r0 && col < a.ncol;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const double r = __shfl_sync(0xffffffffu, tau[i], (lane + 31) & 31);
+            double prev = r;
+            if (lane == 0) {
+                prev = carry_s[i];
+                carry_s[i] = r;
+            }
+            dw[i] = tau[i] - prev;
+        }
+        reduce9(tau, dw, live, live && !(j == 0 && lane == 0 && y > 0), acc);
+        if (live && a.wss_out) {
+            double* o = a.wss_out + (int64_t)(col - a.r0) * a.ws_col + f * a.ws_f;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) o[i * a.ws_i] = tau[i];
+        }
+        if (col == a.ncol - 1) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) a.tau_last_out[(int64_t)i * nF + f] = tau[i];
+        }
+        if ((j == 0 && lane == 0 && y > 0) || (j == nt - 1 && lane == 31)) {
+            double* b = sg.bnd + ((int64_t)(2 * y + (lane == 0 ? 0 : 1)) * 9) * T.n_work + w;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) b[(int64_t)i * T.n_work] = tau[i];
+        }
+    }
+    store_partials(acc, sg.part + (int64_t)y * VH_NSUM * T.n_work + w, T.n_work, a.inv_dt, lane);
+}
+
 // Facets whose cell owns several exterior facets (work[multi_start, n_work)): tau = -mu M^T u with the dense operator
 // K0 built (SurfaceProjector's block solve folded with the contributing faces).  The operator is staged once per warp
 // in shared memory, already scaled by -mu; a pass covers 64 columns, lane l owns columns 2 l and 2 l + 1, so every
 // warp-uniform operator read feeds two evaluations.
-template <int ORDER>
+template <int ORDER, int OCC>
 __device__ __forceinline__ void k2_body_multi2(const K2Args& a, const K2Seg& sg, int bx, int y, double* k2_smem) {
     constexpr int N = ORDER == 2 ? 10 : 4, NV = 3 * N;
     const FacetTables& T = a.T;
@@ -366,7 +458,7 @@ __device__ __forceinline__ void k2_body_multi2(const K2Args& a, const K2Seg& sg,
     const int p0 = y * sg.tile_base + min(y, sg.tile_extra);  // passes of 64 columns
     const int np = sg.tile_base + (y < sg.tile_extra ? 1 : 0);
 
-    double* const Ms = k2_smem + (size_t)wib * K2Launch<ORDER>::WARP_DOUBLES;  // [NV][VH_MROW]
+    double* const Ms = k2_smem + (size_t)wib * K2Launch<ORDER, OCC>::WARP_DOUBLES;  // [NV][VH_MROW]
     double* const carry_s = Ms + NV * VH_MROW;
     {
         const double2* Mg = reinterpret_cast<const double2*>(T.m_mat + (size_t)wi * NV * VH_MROW);
@@ -466,6 +558,7 @@ __device__ __forceinline__ void k2_body_multi2(const K2Args& a, const K2Seg& sg,
 // shuffles and the integer work per unit halve.  (The fp64 pipe of an SM retires 2 warp instructions per clock at 8
 // clocks latency, measured with tools/ubench/fp64_lat.cu; with 4 warps per scheduler and one column per lane the
 // kernel issued 0.57 instructions per clock.)
+template <bool PREFETCH>
 __device__ __forceinline__ void k2_body_flat2(const K2Args& a, const K2Seg& sg, int bx, int y) {
     const FacetTables& T = a.T;
     const int64_t nF = T.nF;
@@ -491,7 +584,7 @@ __device__ __forceinline__ void k2_body_flat2(const K2Args& a, const K2Seg& sg, 
             for (int d = 0; d < 3; ++d) dst[3 * k + d] = __ldg(p + 16 * d);
         }
     };
-    fetch(0, vn);
+    if (PREFETCH) fetch(0, vn);
 
     double gr[19];
 #pragma unroll
@@ -510,9 +603,13 @@ __device__ __forceinline__ void k2_body_flat2(const K2Args& a, const K2Seg& sg, 
 
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     for (int j = 0; j < np; ++j) {
+        if (PREFETCH) {
 #pragma unroll
-        for (int q = 0; q < 12; ++q) v[q] = vn[q];
-        if (j + 1 < np) fetch(j + 1, vn);
+            for (int q = 0; q < 12; ++q) v[q] = vn[q];
+            if (j + 1 < np) fetch(j + 1, vn);
+        } else {
+            fetch(j, v);
+        }
         double t0[3], t1[3], d0[3], d1[3];
         tau_p1(G, [&](int q) { return v[q].x; }, a.mu, t0);
         tau_p1(G, [&](int q) { return v[q].y; }, a.mu, t1);
@@ -579,20 +676,22 @@ __device__ __forceinline__ void k2_body_flat2(const K2Args& a, const K2Seg& sg, 
         for (int i = 0; i < VH_NSUM; ++i) p[(int64_t)i * T.n_work] = i < 9 ? acc[i % 3] : i < 12 ? acc[3] : acc[4] * s;
     }}
 
-template <int ORDER>
-__global__ void __launch_bounds__(32 * K2_WARPS, 3) k2_wall(const K2Args a) {
+template <int ORDER, int OCC>
+__global__ void __launch_bounds__(32 * K2_WARPS, (K2Launch<ORDER, OCC>::BLOCKS)) k2_wall(const K2Args a) {
     extern __shared__ __align__(16) double k2_smem[];
     pdl_wait();  // W comes from the K1 just before; part/bnd were read by the K3 before that
     pdl_launch_dependents();
     const int nb_multi = a.multi.gx * a.multi.gy;
     if ((int)blockIdx.x < nb_multi) {
-        k2_body_multi2<ORDER>(a, a.multi, blockIdx.x % a.multi.gx, blockIdx.x / a.multi.gx, k2_smem);
+        k2_body_multi2<ORDER, OCC>(a, a.multi, blockIdx.x % a.multi.gx, blockIdx.x / a.multi.gx, k2_smem);
     } else {
         const int b = blockIdx.x - nb_multi;
         if constexpr (ORDER == 1)
-            k2_body_flat2(a, a.single, b % a.single.gx, b / a.single.gx);
+            k2_body_flat2<(OCC < 4 || OCC == 6)>(a, a.single, b % a.single.gx, b / a.single.gx);
+        else if constexpr (K2Launch<ORDER, OCC>::DIRECT)
+            k2_body_p2_direct(a, a.single, b % a.single.gx, b / a.single.gx, k2_smem, K2Launch<ORDER, OCC>::WARP_DOUBLES);
         else
-            k2_body_p2(a, a.single, b % a.single.gx, b / a.single.gx, k2_smem);
+            k2_body_p2<OCC>(a, a.single, b % a.single.gx, b / a.single.gx, k2_smem);
     }
 }
 
@@ -692,7 +791,7 @@ __global__ void k4_peer_indices(PeerBlocks pb, int world, int rank, int64_t half
                                 int64_t nF, double count, double* __restrict__ red, double* __restrict__ tawss,
                                 double* __restrict__ osi, double* __restrict__ rrt, double* __restrict__ ecap,
                                 double* __restrict__ twssg, double* count_slot, double my_count) {
-    pdl_wait();  // K3 has folded this rank's sums
+    // (launched on its own stream behind an event recorded after K3: this rank's sums are folded)
     // Block 0 first tells every rank "rank `rank` has finished epoch `epoch`": thread q stores the epoch into rank q's
     // arrival counter after a system-scope fence, so everything this GPU wrote before (K3's sums, the snapshot count
     // that rides behind them) is visible to a peer that has seen the counter.
@@ -713,11 +812,10 @@ __global__ void k4_peer_indices(PeerBlocks pb, int world, int rank, int64_t half
                 flags[VH_MAX_PEERS] = threadIdx.x + 1;
                 break;
             }
-            __nanosleep(100);
+            __nanosleep(20);
         }
     }
     __syncthreads();
-    pdl_launch_dependents();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {  // snapshot count
         double t = 0.0;
@@ -760,13 +858,27 @@ __global__ void k4_peer_indices(PeerBlocks pb, int world, int rank, int64_t half
 int k4_peer_reduce_finalize(vh_handle* h, const PeerBlocks& pb, int64_t half_off, int64_t flags_off, uint64_t epoch,
                             int64_t n_total, double* d_red, double* d_out5) {
     const int64_t nF = h->nF, n3 = 3 * nF;
-    // one launch: block 0 signals this rank's arrival, every block waits for all ranks, then reduces its entries
-    VH_CUDA(vh_launch_pdl(k4_peer_indices, dim3((unsigned)((n3 + 255) / 256)), dim3(256), 0, h->s_compute,
-                          (h->pdl & 8) != 0 && !h->profile, pb, h->world, h->rank, half_off, flags_off, epoch, nF,
-                          (double)n_total, d_red, d_out5, d_out5 + n3, d_out5 + 2 * n3, d_out5 + 3 * n3, d_out5 + 4 * n3,
-                          h->d_sums + VH_NSUM * h->nF, (double)h->count));
+    // One launch: block 0 signals this rank's arrival, every block waits for all ranks, then reduces its entries.  It
+    // runs on s_aux behind this loop's K3, so that the K1/K2 of the next time loop overlap the wait for the peers; the
+    // halves of the sum block alternate between loops, and the next K3 that writes waits for this kernel (vh_join_peer).
+    vh_join_peer(h);  // reductions stay in order, and s_aux never runs two of them at once
+    VH_CUDA(cudaEventRecord(h->ev_fork, h->s_compute));
+    VH_CUDA(cudaStreamWaitEvent(h->s_aux, h->ev_fork, 0));
+    k4_peer_indices<<<dim3((unsigned)((n3 + 255) / 256)), dim3(256), 0, h->s_aux>>>(
+        pb, h->world, h->rank, half_off, flags_off, epoch, nF, (double)n_total, d_red, d_out5, d_out5 + n3, d_out5 + 2 * n3,
+        d_out5 + 3 * n3, d_out5 + 4 * n3, h->d_sums + VH_NSUM * h->nF, (double)h->count);
+    VH_CUDA(cudaGetLastError());
+    VH_CUDA(cudaEventRecord(h->ev_join, h->s_aux));
+    h->peer_pending = true;
     h->launches += 1;
     return VH_OK;
+}
+
+void vh_join_peer(vh_handle* h) {
+    if (h->peer_pending) {
+        cudaStreamWaitEvent(h->s_compute, h->ev_join, 0);
+        h->peer_pending = false;
+    }
 }
 
 FacetTables vh_tables(const vh_handle* h) {
@@ -793,6 +905,9 @@ int k_free_run_buffers(vh_handle* h) {
     if (h->d_part) cudaFree(h->d_part);
     h->out5_count = -1;
     if (h->d_out5) cudaFree(h->d_out5);
+    if (h->d_out5_peer) cudaFree(h->d_out5_peer);
+    h->d_out5_peer = nullptr;
+    h->peer_pending = false;
     if (h->h_out5) cudaFreeHost(h->h_out5);
     h->h_out5 = nullptr;
     h->d_sums = h->d_tau_last[0] = h->d_tau_last[1] = h->d_part = h->d_out5 = nullptr;
@@ -859,23 +974,22 @@ SegPlan plan_segments(int64_t ncol, int64_t pass_cols, int64_t n_items, int64_t 
     return {(int)gy, (int)(total / gy), (int)(total % gy)};
 }
 
-template <int ORDER>
+template <int ORDER, int OCC>
 int launch_k2(vh_handle* h, const K2Args& a, cudaStream_t st, bool pdl) {
-    using L = K2Launch<ORDER>;
+    using L = K2Launch<ORDER, OCC>;
     // function attributes belong to the (function, device) pair: remembered per handle, i.e. per GPU
-    if (!h->k2_configured[ORDER - 1] && L::SMEM_BYTES > 0) {
-        VH_CUDA(cudaFuncSetAttribute(k2_wall<ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES));
-        VH_CUDA(cudaFuncSetAttribute(k2_wall<ORDER>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    bool& configured = h->k2_configured[4 * (ORDER - 1) + (OCC - 3)];
+    if (!configured && L::SMEM_BYTES > 0) {
+        VH_CUDA(cudaFuncSetAttribute(k2_wall<ORDER, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES));
+        VH_CUDA(cudaFuncSetAttribute(k2_wall<ORDER, OCC>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
-        h->k2_configured[ORDER - 1] = true;
+        configured = true;
     }
     const unsigned blocks = (unsigned)(a.multi.gx * a.multi.gy + a.single.gx * a.single.gy);
-    VH_CUDA(vh_launch_pdl(k2_wall<ORDER>, dim3(blocks), dim3(32 * K2_WARPS), L::SMEM_BYTES, st, pdl, a));
+    VH_CUDA(vh_launch_pdl(k2_wall<ORDER, OCC>, dim3(blocks), dim3(32 * K2_WARPS), L::SMEM_BYTES, st, pdl, a));
     return VH_OK;
 }
 
-// resident warps per SM (registers and shared memory, see K2Launch)
-constexpr int K2_RESIDENT_WARPS = 3 * K2_WARPS;
 
 int64_t env_int(const char* name, int64_t dflt) {
     const char* v = getenv(name);
@@ -898,13 +1012,17 @@ int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_el
     // extra segment costs K3), P2 255 / 248 / 251 us
     static const int64_t waves_env = env_int("VASP_B200_K2_WAVES", 0);
     const int64_t waves = waves_env > 0 ? waves_env : (h->order == 1 ? 1 : 2);
+    // blocks per SM the kernel is compiled for (see K2Launch): measured per order, profiles/r2_k2_occupancy.md
+    static const int64_t occ_env = env_int("VASP_B200_K2_OCC", 0);
+    int occ = occ_env >= 3 && occ_env <= 6 ? (int)occ_env : (h->order == 1 ? K2_OCC_P1 : K2_OCC_P2);
+    if (occ == 6 && h->order == 1) occ = 3;  // the direct-load shape only exists for P2
     int64_t pos = 0;
     while (pos < n_snap) {
         const int halo = (pos == 0 && prev_mode == 2) ? 1 : 0;
         int64_t nb = n_snap - pos;
         if (nb + halo > h->w_ld) nb = h->w_ld - halo;
         const int64_t ncol = nb + halo;
-        const int64_t target = (int64_t)h->sm_count * K2_RESIDENT_WARPS * waves;
+        const int64_t target = (int64_t)h->sm_count * (occ == 6 ? 3 : occ) * K2_WARPS * waves;
         const SegPlan ps = plan_segments(ncol, h->order == 1 ? 64 : 32, n_single, target, h->chunk_snapshots);
         // the few multi-facet-cell facets are cut finer and scheduled first, so that they never are the tail
         const SegPlan pm = plan_segments(ncol, 64, n_multi, target / 4, h->chunk_snapshots);
@@ -946,15 +1064,23 @@ int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_el
         a.wss_out = d_wss ? d_wss + pos * a.ws_col : nullptr;
         a.mu = h->mu;
         a.inv_dt = 1.0 / h->dt;
-        if (h->order == 2)
-            VH_TRY(launch_k2<2>(h, a, h->s_compute, (pdl & 2) != 0));
-        else
-            VH_TRY(launch_k2<1>(h, a, h->s_compute, (pdl & 2) != 0));
+        const bool k2_pdl = (pdl & 2) != 0;
+        if (h->order == 2) {
+            if (occ == 6) VH_TRY((launch_k2<2, 6>(h, a, h->s_compute, k2_pdl)));
+            else if (occ == 5) VH_TRY((launch_k2<2, 5>(h, a, h->s_compute, k2_pdl)));
+            else if (occ == 4) VH_TRY((launch_k2<2, 4>(h, a, h->s_compute, k2_pdl)));
+            else VH_TRY((launch_k2<2, 3>(h, a, h->s_compute, k2_pdl)));
+        } else {
+            if (occ == 5) VH_TRY((launch_k2<1, 5>(h, a, h->s_compute, k2_pdl)));
+            else if (occ == 4) VH_TRY((launch_k2<1, 4>(h, a, h->s_compute, k2_pdl)));
+            else VH_TRY((launch_k2<1, 3>(h, a, h->s_compute, k2_pdl)));
+        }
         h->launches += 1;
         if (prof) {
             cudaEventRecord(h->prof_pool[h->prof_used + 2], h->s_compute);
             h->prof_used += 3;
         }
+        vh_join_peer(h);  // K3 writes the running sums: a fused reduction of the loop before last must have read them
         VH_CUDA(vh_launch_pdl(k3_fold, dim3((unsigned)((h->n_work + K3_ITEMS - 1) / K3_ITEMS)), dim3(16 * K3_ITEMS), 0,
                               h->s_compute, (pdl & 4) != 0, h->d_sums, (const double*)a.single.part, (const double*)a.single.bnd,
                               a.single.gy, (const double*)a.multi.part, (const double*)a.multi.bnd, a.multi.gy,

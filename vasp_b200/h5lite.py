@@ -372,8 +372,16 @@ def _dtype_msg(dt: np.dtype) -> bytes:
 
 
 def _space_msg(shape: Tuple[int, ...]) -> bytes:
+    """Dataspace message v1.  Like the library dolfin links (HDF5 1.12, earliest format) a simple dataspace of rank
+    >= 1 carries its maximum dimensions too (flag bit 0; equal to the current ones: nothing here is extendible)."""
     rank = len(shape)
-    return struct.pack("<BBBB4x", 1, rank, 0, 0) + b"".join(struct.pack("<Q", int(d)) for d in shape)
+    dims = b"".join(struct.pack("<Q", int(d)) for d in shape)
+    return struct.pack("<BBBB4x", 1, rank, 1 if rank else 0, 0) + dims + (dims if rank else b"")
+
+
+# object modification time written into dataset headers (message 0x0012 v1, seconds since the epoch): taken once per
+# process, or from SOURCE_DATE_EPOCH, so that the files of one run are reproducible byte for byte
+_MTIME = int(os.environ.get("SOURCE_DATE_EPOCH", 0) or 0) or int(__import__("time").time())
 
 
 def _attr_msg(name: str, value) -> bytes:
@@ -569,12 +577,17 @@ class H5Writer:
     def _write_node(self, node: _WNode) -> None:
         attr_msgs = [_message(0x000C, _attr_msg(k, v)) for k, v in node.attrs.items()]
         if node.is_dataset:
+            # message set, order, versions and flags of a dataset header as dolfin's HDF5 writes them (checked against
+            # the reference's own dolfin-written files: tests/test_h5_structure.py)
             msgs = [
                 _message(0x0001, _space_msg(node.shape)),
                 _message(0x0003, _dtype_msg(node.dtype), flags=1),
-                _message(0x0005, struct.pack("<BBBB", 2, 2, 0, 0)),  # fill value v2: late alloc, undefined
+                # fill value v2 as a serial dolfin run leaves it: space allocated late, fill written "if set", defined
+                # with size 0 (a file written under MPI differs in two places: early allocation, layout flagged constant)
+                _message(0x0005, struct.pack("<BBBBI", 2, 2, 2, 1, 0), flags=1),
                 _message(0x0008, struct.pack("<BBQQ", 3, 1, node.data_addr if node.data_size else _UNDEF,
                                              node.data_size)),
+                _message(0x0012, struct.pack("<B3xI", 1, _MTIME)),
             ] + attr_msgs
         else:
             for ch in node.children.values():
