@@ -322,11 +322,14 @@ def measure(name: str, n_res: int, n_e2e: int, args, rank: int, local_rank: int,
             step_resident()
         total_ms = eng.timer_stop()  # CUDA events on the compute stream; stop synchronises
         launches1 = eng.timers()["launches"]
-        if total_ms < 25.0:  # a short timed region gets a second, untimed stretch so that NVML sees clocks under load
-            t_end = time.perf_counter() + 0.05
-            while time.perf_counter() < t_end:
-                step_resident()
-            eng.sync()
+        # a short timed region gets a second, untimed stretch of ~50 ms so that NVML sees clocks under load (the same
+        # number of steps on every rank: each step is a collective)
+        extra = 0.0 if total_ms >= 25.0 else 50.0 * steps / max(total_ms, 1e-3)
+        if comm:
+            extra = comm.max(extra)
+        for _ in range(int(min(extra, 5000))):
+            step_resident()
+        eng.sync()
         # Same K steps once more with CUDA events between the kernels (per-launch K1/K2 durations for the roofline).
         # The events sit between dependent launches, so this pass runs without programmatic dependent launch and is a
         # few us per step slower than the pass above; `value` comes from the pass above.

@@ -80,3 +80,35 @@ def test_rejects_non_hdf5(tmp_path):
     p.write_bytes(b"not hdf5" * 100)
     with pytest.raises(H5FormatError):
         H5File(p)
+
+
+def test_dataset_table_fast_path_and_fallback(tmp_path):
+    """``h5lite.dataset_table`` lifts offset and timestamp out of like object headers in one numpy pass; a header that
+    differs anywhere else (here: an extra attribute, a continuation-free but longer header) takes the slow parse, and
+    a vector of another length is refused."""
+    from vasp_b200 import io_dolfin
+    from vasp_b200.h5lite import H5File, H5Writer, dataset_table
+    rng = np.random.default_rng(1)
+    data = rng.normal(size=(9, 12))
+    with H5Writer(tmp_path / "u.h5") as w:
+        for k in range(9):
+            attrs = {"timestamp": 0.25 * k, "partition": np.array([0], dtype=np.uint64)}
+            if k == 4:
+                attrs["extra"] = 7.0
+            w.create_dataset(f"/velocity/vector_{k}", data[k], attrs=attrs)
+    with H5File(tmp_path / "u.h5") as f:
+        g = f["velocity"]
+        names = [f"vector_{k}" for k in range(9)]
+        off, ts, _ = dataset_table(g, names, "timestamp")
+        assert np.array_equal(ts, 0.25 * np.arange(9))
+        for k in range(9):
+            assert off[k] == g[names[k]].offset
+            assert np.array_equal(np.frombuffer(f._buf, "<f8", 12, int(off[k])), data[k])
+    s = io_dolfin.VelocitySeries(tmp_path / "u.h5", "velocity", 2)
+    assert list(s.timestamps) == [0.0, 0.5, 1.0, 1.5, 2.0] and s.vec_len == 12
+    s.close()
+    with H5Writer(tmp_path / "bad.h5") as w:
+        w.create_dataset("/velocity/vector_0", data[0], attrs={"timestamp": 0.0})
+        w.create_dataset("/velocity/vector_1", data[1, :7], attrs={"timestamp": 1.0})
+    with pytest.raises(ValueError):
+        io_dolfin.VelocitySeries(tmp_path / "bad.h5", "velocity", 1)

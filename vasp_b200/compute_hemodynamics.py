@@ -314,15 +314,14 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
     # The WSS steps of block i are written (WSS.h5 on rank 0, the shard file elsewhere) by a thread while block i + 1
     # is on the GPU: two result buffers, one being filled by the push, one being drained.
     def store(buf, first_step, n_steps):
-        for r in range(n_steps):
-            k = shard.start + first_step + r
-            t = float(series.timestamps[k])
-            if rank == 0:
-                print("=" * 10, f"Calculating WSS at Timestep: {t}", "=" * 10)
-                # Write temporal WSS
-                wss_writer.write(buf[r], t)
-            else:
-                shard_file[first_step + r] = buf[r]
+        k0 = shard.start + first_step
+        ts = [float(t) for t in series.timestamps[k0:k0 + n_steps]]
+        if rank == 0:
+            print("".join(f"========== Calculating WSS at Timestep: {t} ==========\n" for t in ts), end="")
+            # Write temporal WSS: the whole block of steps in one write
+            wss_writer.write_block(buf[:n_steps], ts)
+        else:
+            shard_file[first_step:first_step + n_steps] = buf[:n_steps]
 
     drain = _Drain(store)
     wss_bufs = [wss_buf, pinned_empty(wss_buf.shape)] if wss_buf is not None else [None, None]
@@ -365,8 +364,9 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
             part = hemodynamic_indices_path / f".WSS_shard{r}.npy"
             if sh.count:
                 arr = np.load(part, mmap_mode="r")
-                for i in range(sh.count):
-                    wss_writer.write(arr[i], float(series.timestamps[sh.start + i]))
+                for i in range(0, sh.count, 256):
+                    j = min(i + 256, sh.count)
+                    wss_writer.write_block(arr[i:j], [float(t) for t in series.timestamps[sh.start + i:sh.start + j]])
                 del arr
                 part.unlink()
         wss_writer.close()

@@ -926,7 +926,7 @@ int k_free_run_buffers(vh_handle* h) {
     return VH_OK;
 }
 
-// Columns per staged block: as many as fit ~1/8 of the free memory (at most 4 GiB), between 64 and 4096; a
+// Columns per staged block: as many as fit ~1/8 of the free memory (at most 8 GiB), between 64 and 4096; a
 // batch_snapshots tuning value caps it (one column more than the batch, for the halo)
 static int ensure_stage_block(vh_handle* h, int64_t want_cols) {
     int64_t cap = h->w_ld;
@@ -936,7 +936,7 @@ static int ensure_stage_block(vh_handle* h, int64_t want_cols) {
     VH_CUDA(cudaMemGetInfo(&free_b, &total_b));
     if (h->d_W) free_b += (size_t)(h->nWn_pad * 24 * h->w_ld);
     int64_t budget = (int64_t)(free_b / 8);
-    if (budget > (4LL << 30)) budget = 4LL << 30;
+    if (budget > (8LL << 30)) budget = 8LL << 30;
     int64_t cols = budget / (h->nWn_pad * 24);
     if (cols > 4096) cols = 4096;
     if (cols > want_cols) cols = want_cols;

@@ -96,18 +96,24 @@ class _Msg:
 class H5Object:
     """A group or dataset, addressed by its object-header offset."""
 
-    def __init__(self, f: "H5File", addr: int, name: str):
+    def __init__(self, f: "H5File", addr: int, name: str, msgs: Optional[List["_Msg"]] = None):
         self._f = f
         self.addr = addr
         self.name = name
-        self._msgs = f._read_header(addr)
+        self._msgs = f._read_header(addr) if msgs is None else msgs
         self._attrs: Optional[Dict[str, np.ndarray]] = None
 
     # -- attributes --------------------------------------------------------------------------------
+    def attr_value_offset(self, name: str) -> Optional[int]:
+        """Absolute file offset of the value of attribute ``name`` (``None`` if absent)."""
+        self.attrs
+        return self._attr_pos.get(name)
+
     @property
     def attrs(self) -> Dict[str, np.ndarray]:
         if self._attrs is None:
             self._attrs = {}
+            self._attr_pos: Dict[str, int] = {}
             buf = self._f._buf
             for m in self._msgs:
                 if m.type != 0x000C:
@@ -128,6 +134,7 @@ class H5Object:
                 count = int(np.prod(shape)) if shape else 1
                 val = np.frombuffer(buf, dtype=dt, count=count, offset=p).copy()
                 self._attrs[aname] = val.reshape(shape) if shape else val.reshape(())
+                self._attr_pos[aname] = p
         return self._attrs
 
     def _find(self, mtype: int) -> Optional[_Msg]:
@@ -146,8 +153,8 @@ class H5Object:
 
 
 class H5Dataset(H5Object):
-    def __init__(self, f: "H5File", addr: int, name: str):
-        super().__init__(f, addr, name)
+    def __init__(self, f: "H5File", addr: int, name: str, msgs: Optional[List["_Msg"]] = None):
+        super().__init__(f, addr, name, msgs)
         buf = f._buf
         ms, mt, ml = self._find(0x0001), self._find(0x0003), self._find(0x0008)
         if ms is None or mt is None or ml is None:
@@ -193,8 +200,8 @@ class H5Dataset(H5Object):
 
 
 class H5Group(H5Object):
-    def __init__(self, f: "H5File", addr: int, name: str):
-        super().__init__(f, addr, name)
+    def __init__(self, f: "H5File", addr: int, name: str, msgs: Optional[List["_Msg"]] = None):
+        super().__init__(f, addr, name, msgs)
         m = self._find(0x0011)
         if m is None:
             raise H5FormatError(f"{name}: not an old-style group")
@@ -263,6 +270,55 @@ class H5Group(H5Object):
         return node
 
 
+def dataset_table(group: "H5Group", names: List[str], attr: str) -> Tuple[np.ndarray, np.ndarray, List["H5Dataset"]]:
+    """``(data offsets, float64 values of scalar attribute attr)`` of many like datasets of one group, plus the
+    first dataset parsed in full.
+
+    A time series holds thousands of datasets written by the same code path: their object headers are byte-for-byte
+    equal except for the data address, the attribute's value and the modification time.  The first header is parsed
+    normally; the others are compared with it as one numpy block and only the two fields are lifted out.  Any header
+    that differs anywhere else (another shape, another attribute set, a continuation block) is parsed the slow way.
+    """
+    f = group._f
+    links = group._load()
+    first = group[names[0]]
+    if not isinstance(first, H5Dataset):
+        raise KeyError(f"{names[0]}: not a dataset")
+    n = len(names)
+    offsets = np.empty(n, dtype=np.int64)
+    values = np.empty(n, dtype=np.float64)
+    offsets[0], values[0] = first.offset, float(first.attrs[attr])
+    slow = list(range(1, n))
+    p0 = f.base + links[names[0]]
+    hsize = struct.unpack_from("<I", f._buf, p0 + 8)[0]
+    ml, at = first._find(0x0008), first.attr_value_offset(attr)
+    simple = (not first.compact and all(m.type != 0x0010 for m in first._msgs) and at is not None
+              and first.attrs[attr].dtype == np.dtype("<f8") and first.attrs[attr].shape == ())
+    if simple and n > 1:
+        span = 16 + hsize
+        raw = np.frombuffer(f._buf, dtype=np.uint8)
+        starts = np.array([f.base + links[nm] for nm in names], dtype=np.int64)
+        ok = starts + span <= raw.size
+        H = raw[np.where(ok, starts, 0)[:, None] + np.arange(span)[None, :]]
+        rel_addr, rel_val = ml.pos + 2 - p0, at - p0
+        mask = np.ones(span, dtype=bool)
+        mask[rel_addr:rel_addr + 8] = False
+        mask[rel_val:rel_val + 8] = False
+        mt = first._find(0x0012)
+        if mt is not None:
+            mask[mt.pos - p0 + 4:mt.pos - p0 + 8] = False
+        same = ok & (H[:, mask] == H[0, mask]).all(axis=1)
+        offsets[same] = np.ascontiguousarray(H[same, rel_addr:rel_addr + 8]).view("<u8").ravel().astype(np.int64) + f.base
+        values[same] = np.ascontiguousarray(H[same, rel_val:rel_val + 8]).view("<f8").ravel()
+        slow = [i for i in np.nonzero(~same)[0] if i != 0]
+    for i in slow:
+        d = group[names[i]]
+        if d.shape != first.shape or d.dtype != first.dtype:
+            raise H5FormatError(f"{names[i]}: shape/type {d.shape} {d.dtype} differs from {names[0]}")
+        offsets[i], values[i] = d.offset, float(d.attrs[attr])
+    return offsets, values, [first]
+
+
 class H5File(H5Group):
     """Read-only view of an HDF5 file (the subset described in the module docstring)."""
 
@@ -328,11 +384,12 @@ class H5File(H5Group):
 
     def _open(self, addr: int, name: str) -> Union[H5Group, H5Dataset]:
         if addr not in self._cache:
-            probe = H5Object(self, addr, name)
-            if probe.is_group:
-                obj: H5Object = H5Group(self, addr, name)
-            elif probe.is_dataset:
-                obj = H5Dataset(self, addr, name)
+            msgs = self._read_header(addr)  # parsed once, handed to the object
+            types = {m.type for m in msgs}
+            if 0x0011 in types:
+                obj: H5Object = H5Group(self, addr, name, msgs)
+            elif 0x0008 in types:
+                obj = H5Dataset(self, addr, name, msgs)
             else:
                 raise H5FormatError(f"{name}: neither old-style group nor dataset")
             self._cache[addr] = obj
@@ -408,9 +465,9 @@ def _message(mtype: int, body: bytes, flags: int = 0) -> bytes:
     return struct.pack("<HHB3x", mtype, len(body), flags) + body
 
 
-def _object_header(msgs: List[bytes]) -> bytes:
+def _object_header(msgs: List[bytes], refcount: int = 1) -> bytes:
     payload = b"".join(msgs)
-    return struct.pack("<BBHII4x", 1, 0, len(msgs), 1, len(payload)) + payload
+    return struct.pack("<BBHII4x", 1, 0, len(msgs), refcount, len(payload)) + payload
 
 
 @dataclass
@@ -424,8 +481,10 @@ class _WNode:
     dtype: Optional[np.dtype] = None
     data_addr: int = 0
     data_size: int = 0
+    nlinks: int = 1          # hard links to this object (its header is written once, with this reference count)
     # filled at close
     header_addr: int = 0
+    written: bool = False
 
 
 class H5Writer:
@@ -447,6 +506,10 @@ class H5Writer:
         self._pos = self._SB_SIZE
         self._root = _WNode("/")
         self._closed = False
+        self._meta: Optional[bytearray] = None   # metadata is assembled in memory at close() and written in one piece
+        self._meta_base = 0
+        self._hdr_cache: Dict[tuple, Tuple[bytes, int]] = {}
+        self._heap_cache: Dict[tuple, Tuple[bytes, Dict[str, int], int]] = {}
 
     # -- tree helpers ----------------------------------------------------------------------------------
     def _node(self, path: str, create: bool = True) -> _WNode:
@@ -486,6 +549,12 @@ class H5Writer:
         pnode = self._node(parent)
         if leaf in pnode.children:
             raise ValueError(f"{path} already exists")
+        if alias_of is not None and not attrs:
+            # same bytes, same header: a hard link to the object already written (one header, reference count + 1)
+            src = self._lookup(alias_of)
+            src.nlinks += 1
+            pnode.children[leaf] = src
+            return src.data_addr, src.data_size
         node = _WNode(leaf, is_dataset=True)
         if alias_of is not None:
             src = self._lookup(alias_of)
@@ -502,6 +571,40 @@ class H5Writer:
         pnode.children[leaf] = node
         return node.data_addr, node.data_size
 
+    def link(self, path: str, target: str) -> None:
+        """Hard link: ``path`` becomes another name of the existing object ``target`` (group or dataset)."""
+        parent, _, leaf = path.rstrip("/").rpartition("/")
+        pnode = self._node(parent)
+        if leaf in pnode.children:
+            raise ValueError(f"{path} already exists")
+        src = self._lookup(target)
+        src.nlinks += 1
+        pnode.children[leaf] = src
+
+    def create_dataset_block(self, paths: List[str], rows: np.ndarray, shape: Optional[Tuple[int, ...]] = None) -> None:
+        """``len(paths)`` datasets whose raw data are the consecutive rows of ``rows`` -- ONE write for the whole
+        block (the per-step vectors of a checkpoint series arrive from the GPU as such a block).  ``shape``: shape of
+        each dataset (default: the row shape)."""
+        arr = np.ascontiguousarray(rows)
+        if arr.dtype.byteorder == ">":
+            arr = arr.astype(arr.dtype.newbyteorder("<"))
+        n = len(paths)
+        if arr.shape[0] != n:
+            raise ValueError("one row per dataset")
+        row_bytes = arr.nbytes // max(n, 1)
+        if row_bytes % 8:
+            raise ValueError("rows must be a multiple of 8 bytes (dataset addresses are 8-byte aligned)")
+        base = self._alloc(arr.nbytes)
+        self._fh.write(memoryview(arr).cast("B") if arr.nbytes else b"")
+        shp = tuple(shape) if shape is not None else arr.shape[1:]
+        for k, path in enumerate(paths):
+            parent, _, leaf = path.rstrip("/").rpartition("/")
+            pnode = self._node(parent)
+            if leaf in pnode.children:
+                raise ValueError(f"{path} already exists")
+            pnode.children[leaf] = _WNode(leaf, is_dataset=True, shape=shp, dtype=arr.dtype,
+                                          data_addr=base + k * row_bytes, data_size=row_bytes)
+
     def _lookup(self, path: str) -> _WNode:
         node = self._root
         for part in [p for p in path.split("/") if p]:
@@ -513,24 +616,35 @@ class H5Writer:
 
     # -- serialisation -----------------------------------------------------------------------------------
     def _emit(self, blob: bytes) -> int:
-        addr = self._alloc(len(blob))
-        self._fh.write(blob)
+        meta = self._meta
+        pad = (-len(meta)) % 8
+        if pad:
+            meta += b"\0" * pad
+        addr = self._meta_base + len(meta)
+        meta += blob
         return addr
 
     def _write_group_index(self, node: _WNode) -> Tuple[int, int]:
         """Local heap + SNODs + B-tree for one group; returns (btree addr, heap addr)."""
         names = sorted(node.children.keys(), key=lambda s: s.encode())
-        heap = bytearray(8)  # offset 0: empty string (B-tree key 0)
-        offs: Dict[str, int] = {}
-        for n in names:
-            offs[n] = len(heap)
-            b = n.encode() + b"\0"
-            heap += b.ljust(_pad8(len(b)), b"\0")
-        # libhdf5 wants a free block it can describe (>= 16 bytes) or H5HL_FREE_NULL (=1)
-        free_off = len(heap)
-        heap += struct.pack("<QQ", 1, 16)
-        data_addr = self._emit(bytes(heap))
-        heap_addr = self._emit(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap), free_off, data_addr))
+        key = tuple(names)
+        cached = self._heap_cache.get(key)   # the step groups of a checkpoint series all have the same member names
+        if cached is None:
+            heap = bytearray(8)  # offset 0: empty string (B-tree key 0)
+            offs: Dict[str, int] = {}
+            for n in names:
+                offs[n] = len(heap)
+                b = n.encode() + b"\0"
+                heap += b.ljust(_pad8(len(b)), b"\0")
+            # libhdf5 wants a free block it can describe (>= 16 bytes) or H5HL_FREE_NULL (=1)
+            free_off = len(heap)
+            heap += struct.pack("<QQ", 1, 16)
+            cached = (bytes(heap), offs, free_off)
+            if len(names) <= 16:
+                self._heap_cache[key] = cached
+        heap_blob, offs, free_off = cached
+        data_addr = self._emit(heap_blob)
+        heap_addr = self._emit(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_blob), free_off, data_addr))
 
         cap = 2 * self.LEAF_K
         snod_size = 8 + cap * 40
@@ -553,7 +667,7 @@ class H5Writer:
         kids = leaves
         while True:
             groups = [kids[i:i + fan] for i in range(0, len(kids), fan)]
-            addr0 = self._alloc(node_size * len(groups))
+            addr0 = self._emit(b"")  # the level's nodes follow each other from the next 8-byte boundary
             addrs = [addr0 + gi * node_size for gi in range(len(groups))]  # siblings link to each other
             nxt: List[Tuple[int, int]] = []
             first_key = 0
@@ -568,13 +682,27 @@ class H5Writer:
                 first_key = grp[-1][1]
                 blob += bytes(body).ljust(node_size, b"\0")
                 nxt.append((addrs[gi], grp[-1][1]))
-            self._fh.write(bytes(blob))
+            got = self._emit(bytes(blob))
+            assert got == addr0
             if len(nxt) == 1:
                 return nxt[0][0], heap_addr
             kids = nxt
             level += 1
 
     def _write_node(self, node: _WNode) -> None:
+        if node.written:   # reached through another hard link already
+            return
+        node.written = True
+        if node.is_dataset and not node.attrs:
+            # attribute-less datasets of one shape and type (the vectors of a series) differ in their data address only
+            key = (node.shape, node.dtype.str, node.data_size, node.nlinks)
+            tpl = self._hdr_cache.get(key)
+            if tpl is not None:
+                blob, at = tpl
+                hdr = bytearray(blob)
+                struct.pack_into("<Q", hdr, at, node.data_addr if node.data_size else _UNDEF)
+                node.header_addr = self._emit(bytes(hdr))
+                return
         attr_msgs = [_message(0x000C, _attr_msg(k, v)) for k, v in node.attrs.items()]
         if node.is_dataset:
             # message set, order, versions and flags of a dataset header as dolfin's HDF5 writes them (checked against
@@ -595,13 +723,21 @@ class H5Writer:
             bt, hp = self._write_group_index(node)
             node._index = (bt, hp)  # type: ignore[attr-defined]
             msgs = [_message(0x0011, struct.pack("<QQ", bt, hp))] + attr_msgs
-        node.header_addr = self._emit(_object_header(msgs))
+        blob = _object_header(msgs, node.nlinks)
+        node.header_addr = self._emit(blob)
+        if node.is_dataset and not node.attrs:
+            at = blob.index(struct.pack("<BBQ", 3, 1, node.data_addr if node.data_size else _UNDEF)) + 2
+            self._hdr_cache[(node.shape, node.dtype.str, node.data_size, node.nlinks)] = (blob, at)
 
     def close(self) -> None:
         if self._closed:
             return
+        self._meta_base = self._alloc(0)
+        self._meta = bytearray()
         self._write_node(self._root)
         bt, hp = self._root._index  # type: ignore[attr-defined]
+        self._fh.write(self._meta)
+        self._pos = self._meta_base + len(self._meta)
         eof = self._alloc(0)
         sb = _SIG + struct.pack("<BBBBBBBB", 0, 0, 0, 0, 0, 8, 8, 0)
         sb += struct.pack("<HHI", self.LEAF_K, self.INTERNAL_K, 0)

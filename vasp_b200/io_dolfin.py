@@ -19,7 +19,7 @@ from typing import List, Sequence, Tuple, Union
 
 import numpy as np
 
-from .h5lite import H5File, H5Writer
+from .h5lite import H5File, H5FormatError, H5Writer, dataset_table
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -79,15 +79,14 @@ class VelocitySeries:
         g = self._f[group]
         self.group = group
         self.names = get_dataset_names(g, step=stride)
-        self._ds = [g[n] for n in self.names]
-        lens = {d.shape for d in self._ds}
-        if len(lens) != 1:
-            raise ValueError(f"{path}: velocity vectors differ in shape: {lens}")
+        try:
+            # one numpy pass over the object headers (they differ in data address and timestamp only)
+            self.offsets, self.timestamps, self._ds = dataset_table(g, self.names, "timestamp")
+        except H5FormatError as e:
+            raise ValueError(f"{path}: velocity vectors differ: {e}") from e
         self.vec_len = int(np.prod(self._ds[0].shape))
         if self._ds[0].dtype != np.dtype("<f8"):
             raise ValueError(f"{path}: vectors must be little-endian float64, got {self._ds[0].dtype}")
-        self.offsets = np.array([d.offset for d in self._ds], dtype=np.int64)
-        self.timestamps = np.array([float(d.attrs["timestamp"]) for d in self._ds])
         self._g = g
 
     def __len__(self) -> int:
@@ -249,23 +248,40 @@ class CheckpointWriter:
         self._times: List[float] = []
 
     def write(self, values: np.ndarray, time: float) -> None:
-        k = len(self._times)
-        base = f"/{self.name}/{self.name}_{k}"
+        vec = np.ascontiguousarray(values, dtype="<f8").reshape(1, -1)
+        self.write_block(vec, [time])
+
+    def write_block(self, values: np.ndarray, times: Sequence[float]) -> None:
+        """``len(times)`` consecutive steps at once: ``values`` is ``(n, dofs...)``, e.g. the block of per-step WSS
+        vectors a push returned -- its bytes go to the file in one write, each step's ``vector`` dataset points into
+        them."""
+        n = len(times)
+        if n == 0:
+            return
+        vals = np.asarray(values)
+        if vals.dtype != np.dtype("<f8") or not vals.flags.c_contiguous:
+            vals = np.ascontiguousarray(vals, dtype="<f8")
+        vals = vals.reshape(vals.shape[0], -1)[:n]
+        ndofs = 3 * self.ncomp * self.nF
+        if vals.shape != (n, ndofs):
+            raise ValueError(f"{self.name}: expected {n} x {ndofs} dofs, got {vals.shape}")
+        k0 = len(self._times)
         first = f"/{self.name}/{self.name}_0"
-        vec = np.ascontiguousarray(values, dtype="<f8").reshape(-1, 1)
-        if vec.shape[0] != 3 * self.ncomp * self.nF:
-            raise ValueError(f"{self.name}: expected {3 * self.ncomp * self.nF} dofs, got {vec.shape[0]}")
-        if k == 0:
-            self._w.create_dataset(f"{base}/mesh/topology", self._btopo, attrs={"celltype": "triangle"})
-            self._w.create_dataset(f"{base}/mesh/geometry", self._bgeom)
-            self._w.create_dataset(f"{base}/cell_dofs", self._cell_dofs)
-            self._w.create_dataset(f"{base}/x_cell_dofs", self._x)
-            self._w.create_dataset(f"{base}/cells", self._cells)
-        else:  # dolfin re-writes the (identical) mesh and dof tables every step; share the bytes instead
-            for member in ("mesh/topology", "mesh/geometry", "cell_dofs", "x_cell_dofs", "cells"):
-                self._w.create_dataset(f"{base}/{member}", None, alias_of=f"{first}/{member}")
-        self._w.create_dataset(f"{base}/vector", vec)
-        self._times.append(float(time))
+        if k0 == 0:
+            self._w.create_dataset(f"{first}/mesh/topology", self._btopo, attrs={"celltype": "triangle"})
+            self._w.create_dataset(f"{first}/mesh/geometry", self._bgeom)
+            self._w.create_dataset(f"{first}/cell_dofs", self._cell_dofs)
+            self._w.create_dataset(f"{first}/x_cell_dofs", self._x)
+            self._w.create_dataset(f"{first}/cells", self._cells)
+        for k in range(max(k0, 1), k0 + n):
+            # dolfin re-writes the (identical) mesh and dof tables every step; here every later step links to the
+            # objects of step 0 (HDF5 hard links: same paths, same content, written once)
+            base = f"/{self.name}/{self.name}_{k}"
+            for member in ("mesh", "cell_dofs", "x_cell_dofs", "cells"):
+                self._w.link(f"{base}/{member}", f"{first}/{member}")
+        self._w.create_dataset_block([f"/{self.name}/{self.name}_{k}/vector" for k in range(k0, k0 + n)], vals,
+                                     shape=(ndofs, 1))
+        self._times.extend(float(t) for t in times)
 
     def close(self) -> None:
         self._w.close()
