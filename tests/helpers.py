@@ -116,6 +116,9 @@ def write_turtle_folder(tmp: Path, u_of_points, n_snap: int, dt: float, mu, save
     vecs = []
     files = ["velocity.h5"] + (["velocity_run_1.h5"] if split_at else [])
     writers = [H5Writer(tmp / "Visualization" / f) for f in files]
+    # turtleFSI stores the mesh its arrays are indexed by once, with the first step (XDMFFile.write)
+    writers[0].create_dataset("/Mesh/0/mesh/geometry", coords.astype("<f8"))
+    writers[0].create_dataset("/Mesh/0/mesh/topology", topo[order], attrs={"celltype": "tetrahedron"})
     items = []
     for k, t in enumerate(times):
         uf = np.asarray(u_of_points(rx, t)).reshape(3, n_ref).T        # (n_ref, 3)

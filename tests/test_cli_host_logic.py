@@ -162,3 +162,24 @@ def test_block_reader_in_compact_mode_handles_ragged_blocks(cpu_engine, tmp_path
         for k in range(3):
             assert np.array_equal(c[:, k * nwp:k * nwp + len(sl)], vecs[a:b, k * n + sl])
     series.close()
+
+
+def test_derived_refined_numbering_needs_no_refined_mesh_files(cpu_engine, tmp_path, capsys):
+    """with --derive-refined-mesh the raw route matches the P2 nodes of mesh_fluid.h5 against the
+    geometry stored in Visualization/velocity.h5; mesh_refined.h5 and mesh_refined_fluid.h5 (the products of
+    create_refined_mesh.py:50-151 and separate_mesh.py:56-107) can be absent.  Same output files as the route that
+    uses them."""
+    a, b = tmp_path / "with", tmp_path / "without"
+    for d in (a, b):
+        d.mkdir()
+        H.write_turtle_folder(d, _u_syn(4), n_snap=6, dt=0.01, mu=3.5e-3, save_step=5, split_at=4)
+    (b / "Mesh" / "mesh_refined.h5").unlink()
+    (b / "Mesh" / "mesh_refined_fluid.h5").unlink()
+    ch.main(["--folder", str(a)])
+    with pytest.raises(AssertionError, match="mesh_refined.h5 not found"):
+        ch.main(["--folder", str(b)])                        # the reference's behaviour stays the default
+    ch.main(["--folder", str(b), "--derive-refined-mesh"])
+    capsys.readouterr()
+    for name in ch.INDEX_NAMES:
+        assert (a / "Hemodynamic_indices" / f"{name}.h5").read_bytes() == \
+            (b / "Hemodynamic_indices" / f"{name}.h5").read_bytes(), name

@@ -100,8 +100,9 @@ def test_parse_arguments_matches_the_reference_parser():
         ns = vars(ch.parse_arguments(argv))
         got = {k: (str(v) if isinstance(v, Path) else v) for k, v in ns.items() if k in want}
         assert got == want, argv
-        assert set(ns) - set(want) == {"velocity_degree", "device"}      # the two documented extensions
-        assert ns["velocity_degree"] == 2 and ns["device"] is None       # ... default to the reference behaviour
+        assert set(ns) - set(want) == {"velocity_degree", "device", "derive_refined_mesh"}   # the documented extensions
+        assert ns["velocity_degree"] == 2 and ns["device"] is None and ns["derive_refined_mesh"] is False  # ... default
+        # to the reference behaviour
 
 
 @pytest.mark.parametrize("name", ["cylinder", "stenosis"])

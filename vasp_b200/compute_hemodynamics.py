@@ -57,6 +57,10 @@ def parse_arguments(argv=None) -> argparse.Namespace:
                         help="2 (reference behaviour: P1 data on the refined mesh = P2 on the mesh) or 1 (P1 data on "
                              "the un-refined mesh; the reference refuses save_deg != 2)")
     parser.add_argument("--device", type=int, default=None, help="CUDA device (default: LOCAL_RANK)")
+    parser.add_argument("--derive-refined-mesh", action="store_true",
+                        help="raw turtleFSI input only: take the node coordinates from Visualization/velocity.h5 "
+                             "instead of Mesh/mesh_refined.h5 and Mesh/mesh_refined_fluid.h5 (vasp-refine-mesh and "
+                             "vasp-separate-mesh need not have been run on the refined mesh)")
     return parser.parse_args(argv)
 
 
@@ -250,7 +254,13 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
 
     if rank == 0:
         print("--- Define function spaces \n")
-    if velocity_degree == 2:
+    if velocity_degree == 2 and getattr(series, "geometry", None) is not None:
+        # (extension) the raw turtleFSI arrays carry the geometry they are indexed by: the P2 nodes of
+        # the wall cells are matched against it directly and <mesh>_refined_fluid.h5 is not needed
+        rxyz = series.geometry
+        comp_offset, node_stride, perm = series.layout(None, len(rxyz))
+        eng.set_velocity_layout(2, refined_xyz=rxyz, node_perm=perm, comp_offset=comp_offset, node_stride=node_stride)
+    elif velocity_degree == 2:
         refined_mesh_path = mesh_path.parent / f"{mesh_name}_refined_fluid.h5"
         assert refined_mesh_path.exists(), f"Mesh file {refined_mesh_path} not found."
         rxyz, rtets = io_dolfin.read_mesh(refined_mesh_path, "mesh")
@@ -441,7 +451,10 @@ def main(argv=None) -> None:
         fluid_domain_id = parameters["dx_f_id"]
         solid_domain_id = parameters["dx_s_id"]
         logging.info(f"--- Fluid domain ID: {fluid_domain_id} and Solid domain ID: {solid_domain_id} \n")
-        if args.mesh_path:
+        if args.derive_refined_mesh:
+            domain_mesh_path = None
+            logging.info("--- Taking the node coordinates from the velocity file \n")
+        elif args.mesh_path:
             domain_mesh_path = Path(args.mesh_path)
             logging.info("--- Using user-defined mesh \n")
             assert domain_mesh_path.exists(), f"Mesh file {domain_mesh_path} not found."
@@ -457,7 +470,8 @@ def main(argv=None) -> None:
             print(f"save_time_step: {save_time_step} \n")
             print("--- Reading the fluid velocity straight from Visualization/velocity.h5 (no u.h5 is written) \n")
         series = io_turtle.TurtleVelocitySeries(visualization_path, domain_mesh_path, save_time_step, args.stride,
-                                                args.start_time, args.end_time, fluid_domain_id, solid_domain_id)
+                                                args.start_time, args.end_time, fluid_domain_id, solid_domain_id,
+                                                **({"derive_refined_mesh": True} if args.derive_refined_mesh else {}))
 
     save_deg = parameters["save_deg"]
     if args.velocity_degree == 2:

@@ -96,7 +96,8 @@ class TurtleVelocitySeries:
 
     def __init__(self, visualization_path: Union[str, Path], mesh_path: Union[str, Path], save_time_step: float,
                  stride: int = 1, start_time: Optional[float] = None, end_time: Optional[float] = None,
-                 fluid_domain_id=1, solid_domain_id=2, compute_stride: Optional[int] = None):
+                 fluid_domain_id=1, solid_domain_id=2, compute_stride: Optional[int] = None,
+                 derive_refined_mesh: bool = False):
         self.path = Path(visualization_path)
         xdmf = self.path / "velocity.xdmf"
         assert xdmf.exists(), f"Velocity file {xdmf} not found."
@@ -106,9 +107,23 @@ class TurtleVelocitySeries:
         steps = select_steps(times, save_time_step, stride, start_time, end_time)
         # ... written as vector_0, vector_1, ... and read back by get_dataset_names(step=stride)
         steps = steps[::(stride if compute_stride is None else compute_stride)]
-        self.fluid_ids, _, all_ids = get_domain_ids(mesh_path, fluid_domain_id, solid_domain_id)
-        self.n_all = int(all_ids.max()) + 1 if len(all_ids) else 0
         self._files = {}
+        self.geometry: Optional[np.ndarray] = None
+        if derive_refined_mesh:
+            # no mesh_refined.h5 / mesh_refined_fluid.h5 needed.  turtleFSI stores the geometry its
+            # arrays are indexed by next to them (/Mesh/0/mesh/geometry of the first file -- the authority
+            # create_refined_mesh.py:64-83 itself renumbers the refined mesh against); the P2 nodes of the fluid mesh
+            # are matched against those coordinates directly (K0), so neither the refinement (create_refined_mesh.py:
+            # 50-151) nor the separation (separate_mesh.py:56-107) has to be run first.
+            f0 = self._files[files[steps[0]]] = H5File(self.path / files[steps[0]])
+            self.geometry = f0["Mesh/0/mesh/geometry"].read().astype(np.float64)
+            if self.geometry.ndim != 2 or self.geometry.shape[1] != 3:
+                raise ValueError(f"{self.path / files[steps[0]]}: /Mesh/0/mesh/geometry must be (N, 3)")
+            self.fluid_ids = None
+            self.n_all = len(self.geometry)
+        else:
+            self.fluid_ids, _, all_ids = get_domain_ids(mesh_path, fluid_domain_id, solid_domain_id)
+            self.n_all = int(all_ids.max()) + 1 if len(all_ids) else 0
         self.names: List[str] = []
         self._fd: List[int] = []
         offsets = []
@@ -140,6 +155,10 @@ class TurtleVelocitySeries:
         """Component c of fluid-mesh vertex v sits at ``c + 3 * fluid_ids[v]`` of a raw array: the vertices of the
         separated fluid mesh are the whole-domain nodes ``unique(fluid topology)`` in ascending order
         (``separate_mesh.py:79-92``)."""
+        if self.fluid_ids is None:  # derived route: the velocity nodes ARE the rows of the raw arrays
+            if n_nodes != self.n_all:
+                raise ValueError(f"{self.path}: the stored geometry has {self.n_all} nodes, asked for {n_nodes}")
+            return (0, 1, 2), 3, None
         if len(self.fluid_ids) != n_nodes:
             raise ValueError(f"{self.path}: the domain table has {len(self.fluid_ids)} fluid nodes, the fluid mesh "
                              f"{n_nodes} vertices")
