@@ -18,6 +18,7 @@ from vasp_b200 import io_dolfin, synth, wss_matrix
 def cpu_engine(monkeypatch):
     monkeypatch.setattr(ch, "HemoEngine", OracleHemoEngine)
     monkeypatch.setattr(ch, "pinned_empty", lambda shape: np.zeros(shape))
+    monkeypatch.setattr(ch, "device_count", lambda: 1)
     monkeypatch.setattr(engine_mod, "pinned_empty", lambda shape: np.zeros(shape))
     for n in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_SIZE", "PMI_RANK", "PMI_SIZE",
               "SLURM_PROCID", "SLURM_NTASKS"):

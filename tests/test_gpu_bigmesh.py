@@ -85,6 +85,7 @@ def test_baseline_p2_meshes_against_the_oracle(engine_lib, name, n_long):
         r = co.run(rows, dt, off, tau_prev=prev, threads=threads)
         prev = r["tau_last"]
         acc = r if acc is None else {k: (acc[k] + r[k] if k != "tau_last" else r[k]) for k in r}
+    eng.set_tuning(batch_snapshots=127)   # W holds at most 128 columns: the push below needs three or four blocks
     launches0 = eng.timers()["launches"]
     eng.begin(bench.MU, dt)
     eng.push_compact_device(d, n_long, 3 * nwp * 8, flags=1)

@@ -169,6 +169,7 @@ def test_entry_point_writes_what_the_reference_function_wrote(tmp_path, monkeypa
     cfg, xyz, tets, rx, rt, vecs, times, S = _loop_case()
     monkeypatch.setattr(ch, "HemoEngine", OracleHemoEngine)
     monkeypatch.setattr(ch, "pinned_empty", lambda shape: np.zeros(shape))
+    monkeypatch.setattr(ch, "device_count", lambda: 1)
     monkeypatch.setattr(engine_mod, "pinned_empty", lambda shape: np.zeros(shape))
     for n_ in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         monkeypatch.delenv(n_, raising=False)

@@ -120,7 +120,8 @@ from vasp_b200 import compute_hemodynamics as ch, engine as engine_mod, timeshar
 dist.init_process_group("gloo")
 ch.HemoEngine = OracleHemoEngine
 ch.pinned_empty = engine_mod.pinned_empty = lambda shape: np.zeros(shape)
-ch.NcclComm = lambda eng, rank, world: timeshard.TorchDistComm(eng)
+ch.device_count = lambda: 1
+ch.NcclComm = lambda eng, rank, world, rendezvous_dir=None: timeshard.TorchDistComm(eng)
 ch.main(["--folder", os.environ["FOLDER"]])
 dist.destroy_process_group()
 '''

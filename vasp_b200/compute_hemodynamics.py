@@ -33,7 +33,7 @@ from typing import Dict, Optional, Union
 import numpy as np
 
 from . import io_dolfin, io_turtle
-from .engine import HemoEngine, pinned_empty
+from .engine import HemoEngine, device_count, pinned_empty
 from .timeshard import NcclComm, env_rank_world, plan_shard
 
 INDEX_NAMES = ["RRT", "OSI", "ECAP", "WSS", "TAWSS", "TWSSG"]  # compute_hemodynamics.py:253
@@ -128,13 +128,13 @@ class _Drain:
 
 
 def default_block_snapshots(vec_len: int, compact_len: int = 0) -> int:
-    """Snapshots per pinned read buffer: ~16 MiB, at least 2 and at most 512.  Small blocks matter twice: nothing
+    """Snapshots per pinned read buffer: ~8 MiB, at least 2 and at most 512.  Small blocks matter twice: nothing
     overlaps the first block's read, and pinning memory costs about as much per byte as reading it (measured:
     2 x 260 MB buffers cost more than reading the 1 GB file from the page cache, profiles/r1io_*).  When the wall layer
     is gathered on the way (``compact_len`` doubles per snapshot land in the buffer instead of ``vec_len``) the rows
     are small, and a block should also fill the lanes of the traction kernel: up to 64 snapshots within 1 GiB."""
     row = (compact_len or vec_len) * 8
-    n = (16 << 20) // row
+    n = (8 << 20) // row
     if compact_len:
         n = max(n, min(64, (1 << 30) // row))
     return int(min(512, max(2, n)))
@@ -249,7 +249,11 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
     assert fluid_mesh_path.exists(), f"Mesh file {fluid_mesh_path} not found."
     xyz, tets = io_dolfin.read_mesh(fluid_mesh_path, "mesh")
 
-    eng = HemoEngine(local_rank if device is None else device)
+    if device is None:
+        # one process per GPU: the launcher's local rank picks the device.  Under `srun --gpus-per-task=1` every task
+        # sees a single device 0 whatever its local id is, hence the modulo.
+        device = local_rank % max(device_count(), 1)
+    eng = HemoEngine(device)
     eng.set_mesh(xyz, tets)  # BoundaryMesh(mesh, "exterior") and all index maps, on the device
 
     if rank == 0:
@@ -285,7 +289,8 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
     # Get time difference between two consecutive time steps
     dt = float(series.timestamps[1] - series.timestamps[0])
     eng.begin(mu_f, dt)
-    comm = NcclComm(eng, rank, world) if world > 1 else None
+    # the NCCL id travels through the output folder: every rank must see it anyway (WSS shards are merged from there)
+    comm = NcclComm(eng, rank, world, rendezvous_dir=str(hemodynamic_indices_path)) if world > 1 else None
 
     shard = plan_shard(n_snap, rank, world)
     nF = eng.nF

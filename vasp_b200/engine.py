@@ -44,6 +44,13 @@ def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
     return arr
 
 
+def device_count() -> int:
+    """CUDA devices visible to this process (raises if the library is missing: there is no CPU path)."""
+    n = C.c_int(0)
+    check(_lib.load().vh_device_count(C.byref(n)))
+    return int(n.value)
+
+
 class HemoEngine:
     """One engine per GPU (one process per GPU under a launcher)."""
 

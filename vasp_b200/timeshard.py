@@ -175,16 +175,32 @@ class NcclComm:
     """Device-side reduction (the product path): NCCL for the plumbing, and -- when the ranks share an NVSwitch node
     and can map each other's memory -- the fused peer-memory reduction + final formulas."""
 
-    def __init__(self, engine, rank: int, world: int, peer: bool = True):
+    def __init__(self, engine, rank: int, world: int, peer: bool = True, rendezvous_dir: Optional[str] = None):
+        """``rendezvous_dir``: where rank 0 leaves the NCCL unique id for the others.  The default (``/tmp`` or
+        ``VASP_B200_RDZV_DIR``) only reaches the ranks of one node; launchers that span nodes (``mpirun``, ``srun``:
+        the reference is run as ``mpirun -np N vasp-compute-hemo``, docs/postprocess.md:165) need a directory every
+        rank sees -- the entry point passes its output folder, which has to be shared anyway."""
+        import socket
+        import zlib
         from .engine import HemoEngine, VaspHemoError
         self.engine, self.rank, self.world = engine, rank, world
-        uid = exchange_unique_id(rank, world, HemoEngine.nccl_unique_id)
+        try:
+            uid = exchange_unique_id(rank, world, HemoEngine.nccl_unique_id, directory=rendezvous_dir)
+        except TimeoutError as e:
+            raise TimeoutError(f"{e}.  If the ranks run on several hosts, the rendezvous directory "
+                               f"({rendezvous_dir or os.environ.get('VASP_B200_RDZV_DIR', '/tmp')}) must be on a file "
+                               "system all of them share (set VASP_B200_RDZV_DIR).") from e
         engine.nccl_init(uid, rank, world)
         engine.barrier()
         if rank == 0:
-            cleanup_unique_id(world)
+            cleanup_unique_id(world, rendezvous_dir)
+        # do all ranks sit on one host?  (CUDA IPC peer mappings -- the fused reduction -- only exist inside a node)
+        tag = float(zlib.crc32(socket.gethostname().encode()) % (1 << 24))
+        self.one_host = engine.allreduce_max(tag) == -engine.allreduce_max(-tag)
         self.fused = False
-        if peer and world <= 8 and os.environ.get("VASP_B200_PEER_REDUCE", "1") != "0":
+        if not self.one_host and rank == 0:
+            print("--- ranks span several hosts: reducing with ncclAllReduce (the peer-memory reduction is node-local)")
+        if peer and self.one_host and world <= 8 and os.environ.get("VASP_B200_PEER_REDUCE", "1") != "0":
             try:
                 engine.peer_init()   # collective: fails on every rank or on none
                 self.fused = True
