@@ -365,7 +365,7 @@ def measure(name: str, n_res: int, n_e2e: int, args, rank: int, local_rank: int,
         eng.device_free(d)
 
     # end to end through the public API: pinned host snapshot VECTORS in, five result fields out
-    n_e2e = min(n_e2e, n_mine)
+    n_e2e = int(min(n_e2e, n_mine, max(4, 12e9 // (vec_len * 8))))  # at most ~12 GB of pinned host vectors
     e2e_steps = max(1, min(steps, 10 if headline else 3))
     if os.environ.get("VASP_B200_E2E_BATCH"):  # experiments: snapshots per host->device batch (default: auto)
         eng.set_tuning(batch_snapshots=int(os.environ["VASP_B200_E2E_BATCH"]))

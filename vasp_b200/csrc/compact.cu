@@ -137,6 +137,30 @@ void gather_range(const double* __restrict__ src, const int32_t* __restrict__ sl
     double* o1 = out + ld;
     double* o2 = out + 2 * ld;
     const bool interleaved = off[1] == off[0] + 1 && off[2] == off[0] + 2;  // one line serves the three components
+    static const int scramble = [] {
+        const char* e = getenv("VASP_B200_GATHER_ORDER");
+        return e && *e ? atoi(e) : 0;
+    }();
+    if (scramble && i1 - i0 == GATHER_NODES) {
+        // experiment: visit the nodes of the chunk in a scrambled order (odd multiplier modulo 2^14) so that the
+        // hardware stream prefetchers do not pull in the lines between wall-layer nodes
+        constexpr int64_t M = 6151, MASK = GATHER_NODES - 1;
+        for (int64_t j = 0; j < GATHER_NODES; ++j) {
+            const int64_t ip = i0 + (((j + PREFETCH_AHEAD) * M) & MASK);
+            const int64_t sp = slot[ip];
+            __builtin_prefetch(s0 + sp, 0, 0);
+            if (!interleaved) {
+                __builtin_prefetch(s1 + sp, 0, 0);
+                __builtin_prefetch(s2 + sp, 0, 0);
+            }
+            const int64_t i = i0 + ((j * M) & MASK);
+            const int64_t sl = slot[i];
+            o0[i] = s0[sl];
+            o1[i] = s1[sl];
+            o2[i] = s2[sl];
+        }
+        return;
+    }
     const int64_t ipf = i1 - PREFETCH_AHEAD;
     int64_t i = i0;
     for (; i < ipf; ++i) {
