@@ -149,3 +149,43 @@ def test_raw_turtlefsi_output_gives_the_same_fields_as_u_h5(tmp_path):
     for name in H.FIELDS:
         got = io_dolfin.read_checkpoint(raw / "Hemodynamic_indices", name, 0)["values"]
         assert H.rel_l2(got, fin[name]) < 1e-10, name
+
+
+def test_derived_refined_numbering_on_the_gpu(tmp_path):
+    """SURVEY.md §8f-4 on the real engine: ``--derive-refined-mesh`` matches the P2 nodes of the wall cells against the
+    geometry stored in the raw velocity file (all nodes of the whole domain, solid ones included) instead of
+    ``mesh_refined_fluid.h5``; ``mesh_refined.h5`` / ``mesh_refined_fluid.h5`` are deleted.  Fields and WSS series must be
+    bit-identical to the route that uses them, and within 1e-10 of the oracle."""
+    basis_cache = {}
+
+    def u_syn(p, t):
+        if "b" not in basis_cache:
+            basis_cache["b"] = synth.velocity_basis(p, seed=4)
+        coef = np.array([[1 + 0.5 * np.sin(2 * np.pi * t), 0.3 * np.sin(4 * np.pi * t + 1), 0.2 * np.cos(6 * np.pi * t),
+                          0.1 * np.sin(2 * np.pi * t + 2)]])
+        return synth.velocity_series(basis_cache["b"], coef)[0]
+
+    a, b = tmp_path / "with", tmp_path / "without"
+    for d in (a, b):
+        d.mkdir()
+        info = H.write_turtle_folder(d, u_syn, n_snap=9, dt=0.01, mu=3.5e-3, save_step=5, split_at=6)
+    (b / "Mesh" / "mesh_refined.h5").unlink()
+    (b / "Mesh" / "mesh_refined_fluid.h5").unlink()
+    run = [sys.executable, "-m", "vasp_b200.compute_hemodynamics", "--folder"]
+    subprocess.check_output(run + [str(a)], cwd=ROOT, text=True)
+    assert subprocess.run(run + [str(b)], cwd=ROOT, capture_output=True, text=True).returncode != 0   # reference behaviour
+    subprocess.check_output(run + [str(b), "--derive-refined-mesh"], cwd=ROOT, text=True)
+    for name in H.FIELDS:
+        x = io_dolfin.read_checkpoint(a / "Hemodynamic_indices", name, 0)["values"]
+        y = io_dolfin.read_checkpoint(b / "Hemodynamic_indices", name, 0)["values"]
+        assert np.array_equal(x, y), name
+    for k in range(9):
+        x = io_dolfin.read_checkpoint(a / "Hemodynamic_indices", "WSS", k)["values"]
+        y = io_dolfin.read_checkpoint(b / "Hemodynamic_indices", "WSS", k)["values"]
+        assert np.array_equal(x, y), k
+    case = {"xyz": info["xyz"], "tets": info["tets"], "order": 2, "points": info["rx"], "u": info["vecs"],
+            "dt": 0.05, "n_nodes": len(info["rx"])}
+    _, res, fin = H.oracle_run(case, 3.5e-3)
+    for name in H.FIELDS:
+        y = io_dolfin.read_checkpoint(b / "Hemodynamic_indices", name, 0)["values"]
+        assert H.rel_l2(y, fin[name]) < 1e-10, name

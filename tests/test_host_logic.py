@@ -149,7 +149,9 @@ def test_series_reads_in_pieces_over_a_thread_pool(tmp_path, monkeypatch):
         assert b - a >= 2
         got.append(np.array(u[:, :3 * n]))
     assert np.array_equal(np.concatenate(got), vecs[2:])
-    assert default_block_snapshots(3 * 2997) == 233 and default_block_snapshots(3 * 13_400_000) == 2
+    assert default_block_snapshots(3 * 2997) == 116 and default_block_snapshots(3 * 13_400_000) == 2
+    # compact rows (wall layer gathered on the way): up to 64 snapshots within 1 GiB, so that a block fills K2's lanes
+    assert default_block_snapshots(3 * 13_400_000, 3 * 998_688) == 44 and default_block_snapshots(3 * 351_329, 3 * 70_688) == 64
     s.close()
 
 

@@ -17,7 +17,8 @@ run weak_stenosis_p1 --steps 200 --warmup 3
 run weak_stenosis_p2 --workload stenosis_p2 --steps 50 --warmup 3
 run strong_aneurysm_p1 --workload aneurysm_p1 --snapshots 2000 --scaling strong --steps 5 --warmup 3
 if [ -n "$BIG" ]; then
-  run strong_vessel10m_p2 --workload vessel10m_p2 --snapshots 2000 --scaling strong --steps 3 --warmup 3 $BIG
+  if [ "$BIG" = "--no-parity" ]; then PAR="--no-parity"; else PAR=""; fi
+  run strong_vessel10m_p2 --workload vessel10m_p2 --snapshots 2000 --scaling strong --steps 3 --warmup 3 $PAR
 fi
 python - $OUT $N <<'PY'
 import json,sys,glob

@@ -45,7 +45,13 @@ constexpr double Q_C = 0.47014206410511505, Q_D = 0.05971587178976981;
 constexpr double Q_W0 = 0.225, Q_W1 = 0.12593918054482717, Q_W2 = 0.13239415278850616;
 
 constexpr int K2_WARPS = 4;
-constexpr int K2_OCC_P1 = 3, K2_OCC_P2 = 3;  // default launch shape per order (K2Launch)
+// Default launch shape (K2Launch).  K2 by itself is indifferent to the shape (it is bound by fp64
+// operand bandwidth, not by occupancy), but the whole step is not: with 128 registers the blocks of the next kernel in
+// the programmatic-dependent-launch chain find room earlier.  Measured (profiles/r2_k2_occupancy.md): step 2.95 -> 2.63 ms
+// on the 5 M-tet P2 mesh, 0.724 -> 0.695 ms on the 2 M-tet P1 mesh, 249 -> 243 us on the small P2 mesh, but 55.2 -> 57.7 us
+// on the small P1 mesh (its K2 loses the register double buffer).
+constexpr int K2_OCC_P2 = 4, K2_OCC_P1_LARGE = 4, K2_OCC_P1_SMALL = 3;
+constexpr int64_t K2_P1_LARGE_FACETS = 16384;
 
 // Three code paths share one launch (k2_wall<ORDER>):
 //   k2_body_flat2     P1 data, cell with one exterior facet: values by ld.global.nc straight into registers (register
@@ -96,67 +102,80 @@ __device__ __forceinline__ double sqrt_nb(double x) {
 
 __device__ __forceinline__ double norm3(double a, double b, double c) { return sqrt_nb(fma(a, a, fma(b, b, c * c))); }
 
-// Tangential traction Ft = F - (F.n) n, F = -mu (grad u + grad u^T) n, of P1 data (grad u constant in the cell):
-// G n = sum_b u_b (grad lambda_b . n),  G^T n = sum_b grad lambda_b (u_b . n).  G(i) = {g[4][3], n[3], gam[4]}[i],
-// U(3 b + d) = component d of the velocity at vertex b.
+// Per-facet constants of the closed-form traction, as the kernels hold them in registers (19 doubles):
+//   C(3 b + d) = hh_b[d] = g_b[d] - 2 gamma_b n[d],   C(12 + d) = n[d],   C(15 + b) = gamma_b = g_b . n
+// (g_b = grad lambda_b, n = outward unit normal).  They fold the tangential projection P = I - n n^T into the operator:
+// a dyad u (x) g_b inside grad u contributes  P [(u (x) g_b) + (u (x) g_b)^T] n = gamma_b u + (u . n) hh_b  to the
+// tangential part of (grad u + grad u^T) n, so F . n is never formed and nothing is projected afterwards
+// (9 fp64 instructions fewer per P1 unit, 33 per P2 unit, than forming F and projecting it).
+__device__ __forceinline__ void traction_constants(const FacetTables& T, int32_t f, double (&gr)[19]) {
+    const int64_t nF = T.nF;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) gr[i] = T.glam[(int64_t)i * nF + f];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) gr[12 + d] = T.normal[(int64_t)d * nF + f];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const double gam = gr[3 * b] * gr[12] + gr[3 * b + 1] * gr[13] + gr[3 * b + 2] * gr[14];
+        gr[15 + b] = gam;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) gr[3 * b + d] = fma(-2.0 * gam, gr[12 + d], gr[3 * b + d]);
+    }
+}
+
+// Tangential traction Ft = F - (F.n) n, F = -mu (grad u + grad u^T) n, of P1 data (grad u = sum_b u_b (x) g_b, constant
+// in the cell):  Ft = -mu sum_b [gamma_b u_b + (u_b . n) hh_b].  C(i) as above, U(3 b + d) = component d of the velocity
+// at vertex b.
 template <class GF, class UF>
-__device__ __forceinline__ void tau_p1(GF G, UF U, double mu, double (&ft)[3]) {
-    const double n0 = G(12), n1 = G(13), n2 = G(14);
+__device__ __forceinline__ void tau_p1(GF C, UF U, double mu, double (&ft)[3]) {
+    const double n0 = C(12), n1 = C(13), n2 = C(14);
     double s[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
         const double un = fma(U(3 * b + 2), n2, fma(U(3 * b + 1), n1, U(3 * b) * n0));
 #pragma unroll
-        for (int d = 0; d < 3; ++d) s[d] = fma(U(3 * b + d), G(15 + b), fma(G(3 * b + d), un, s[d]));
+        for (int d = 0; d < 3; ++d) s[d] = fma(U(3 * b + d), C(15 + b), fma(C(3 * b + d), un, s[d]));
     }
-    const double fx = -mu * s[0], fy = -mu * s[1], fz = -mu * s[2];
-    const double fn = fx * n0 + fy * n1 + fz * n2;
-    ft[0] = fma(-fn, n0, fx);
-    ft[1] = fma(-fn, n1, fy);
-    ft[2] = fma(-fn, n2, fz);
+    ft[0] = -mu * s[0];
+    ft[1] = -mu * s[1];
+    ft[2] = -mu * s[2];
 }
 
 // P2 data, cell with one exterior facet: tau[3 V + d] at the facet vertices V = 0, 1, 2.
 //   grad u (v_a) = H + 4 (u_a (x) g_a + sum_{b != a} u_ab (x) g_b),  H = -sum_b u_b (x) g_b
-// Only G n and G^T n are formed.  The constants G(i) and the dof values U(3 k + d) are fetched where they are needed
-// (from registers or shared memory), so that little more than the ten u_k . n stays live.
+// With the projected operator above: tau(V) = mu B - 4 mu S_V,  B = sum_b [gamma_b u_b + (u_b . n) hh_b] over the four
+// vertex dofs, S_V the same sum over (u_V, g_V) and the three edge dofs at V paired with the far vertex's constants.
+// The constants C(i) and the dof values U(3 k + d) are fetched where they are needed (from registers or shared
+// memory), so that little more than the ten u_k . n stays live.
 template <class GF, class UF>
-__device__ __forceinline__ void tau_p2(GF G, UF U, double mu, double (&tau)[9]) {
-    const double n0 = G(12), n1 = G(13), n2 = G(14);
+__device__ __forceinline__ void tau_p2(GF C, UF U, double mu, double (&tau)[9]) {
+    const double n0 = C(12), n1 = C(13), n2 = C(14);
     double un[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) un[k] = fma(U(3 * k + 2), n2, fma(U(3 * k + 1), n1, U(3 * k) * n0));
-    double c[3] = {0.0, 0.0, 0.0};  // (H + H^T) n
+    double mb[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
 #pragma unroll
-        for (int d = 0; d < 3; ++d) c[d] = fma(-U(3 * b + d), G(15 + b), fma(-G(3 * b + d), un[b], c[d]));
+        for (int d = 0; d < 3; ++d) mb[d] = fma(U(3 * b + d), C(15 + b), fma(C(3 * b + d), un[b], mb[d]));
     }
 #pragma unroll
-    for (int V = 0; V < 3; ++V) {
-        double e[3], t[3];
+    for (int d = 0; d < 3; ++d) mb[d] *= mu;
+    const double m4 = -4.0 * mu;
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            e[d] = U(3 * V + d) * G(15 + V);
-            t[d] = G(3 * V + d) * un[V];
-        }
+    for (int V = 0; V < 3; ++V) {
+        double sv[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) sv[d] = fma(U(3 * V + d), C(15 + V), C(3 * V + d) * un[V]);
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             if (b == V) continue;
             const int k = edge_dof(V, b);
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                e[d] = fma(U(3 * k + d), G(15 + b), e[d]);
-                t[d] = fma(G(3 * b + d), un[k], t[d]);
-            }
+            for (int d = 0; d < 3; ++d) sv[d] = fma(U(3 * k + d), C(15 + b), fma(C(3 * b + d), un[k], sv[d]));
         }
-        const double fx = -mu * fma(4.0, e[0] + t[0], c[0]);
-        const double fy = -mu * fma(4.0, e[1] + t[1], c[1]);
-        const double fz = -mu * fma(4.0, e[2] + t[2], c[2]);
-        const double fn = fx * n0 + fy * n1 + fz * n2;
-        tau[3 * V + 0] = fma(-fn, n0, fx);
-        tau[3 * V + 1] = fma(-fn, n1, fy);
-        tau[3 * V + 2] = fma(-fn, n2, fz);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) tau[3 * V + d] = fma(sv[d], m4, mb[d]);
     }
 }
 
@@ -296,14 +315,9 @@ __device__ __forceinline__ void k2_body_p2(const K2Args& a, const K2Seg& sg, int
     };
     fetch(0);
 
-    // per-facet constants in registers: {grad lambda [4][3], n [3], gamma [4]}
+    // per-facet constants in registers (traction_constants): {hh [4][3], n [3], gamma [4]}
     double gr[19];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) gr[i] = T.glam[(int64_t)i * nF + f];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) gr[12 + d] = T.normal[(int64_t)d * nF + f];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) gr[15 + b] = gr[3 * b] * gr[12] + gr[3 * b + 1] * gr[13] + gr[3 * b + 2] * gr[14];
+    traction_constants(T, f, gr);
     // tau_prev of the segment's first column.  Segment 0: zero, or carried over from the last launch; later
     // segments: unknown here -- lane 0 skips that one TWSSG term and k3_fold adds it from the boundary records.
     if (lane == 0) {
@@ -383,12 +397,7 @@ __device__ __forceinline__ void k2_body_p2_direct(const K2Args& a, const K2Seg& 
 #pragma unroll
     for (int k = 0; k < 10; ++k) rb[k] = (T.row[(int64_t)k * nF + f] * a.ntile_ld + t0) * 96 + lane;
     double gr[19];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) gr[i] = T.glam[(int64_t)i * nF + f];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) gr[12 + d] = T.normal[(int64_t)d * nF + f];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) gr[15 + b] = gr[3 * b] * gr[12] + gr[3 * b + 1] * gr[13] + gr[3 * b + 2] * gr[14];
+    traction_constants(T, f, gr);
     if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) carry_s[i] = (y == 0 && a.prev_mode == 1) ? a.tau_last_in[(int64_t)i * nF + f] : 0.0;
@@ -587,12 +596,7 @@ __device__ __forceinline__ void k2_body_flat2(const K2Args& a, const K2Seg& sg, 
     if (PREFETCH) fetch(0, vn);
 
     double gr[19];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) gr[i] = T.glam[(int64_t)i * nF + f];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) gr[12 + d] = T.normal[(int64_t)d * nF + f];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) gr[15 + b] = gr[3 * b] * gr[12] + gr[3 * b + 1] * gr[13] + gr[3 * b + 2] * gr[14];
+    traction_constants(T, f, gr);
     auto G = [&](int i) { return gr[i]; };
 
     // tau_prev of the segment's first column (see k2_body)
@@ -1014,7 +1018,8 @@ int k2_launch(vh_handle* h, const double* d_u, int64_t n_snap, int64_t stride_el
     const int64_t waves = waves_env > 0 ? waves_env : (h->order == 1 ? 1 : 2);
     // blocks per SM the kernel is compiled for (see K2Launch): measured per order, profiles/r2_k2_occupancy.md
     static const int64_t occ_env = env_int("VASP_B200_K2_OCC", 0);
-    int occ = occ_env >= 3 && occ_env <= 6 ? (int)occ_env : (h->order == 1 ? K2_OCC_P1 : K2_OCC_P2);
+    int occ = occ_env >= 3 && occ_env <= 6 ? (int)occ_env
+              : h->order == 2 ? K2_OCC_P2 : (h->nF >= K2_P1_LARGE_FACETS ? K2_OCC_P1_LARGE : K2_OCC_P1_SMALL);
     if (occ == 6 && h->order == 1) occ = 3;  // the direct-load shape only exists for P2
     int64_t pos = 0;
     while (pos < n_snap) {
