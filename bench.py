@@ -366,6 +366,8 @@ def measure(name: str, n_res: int, n_e2e: int, args, rank: int, local_rank: int,
 
     # end to end through the public API: pinned host snapshot VECTORS in, five result fields out
     n_e2e = int(min(n_e2e, n_mine, max(4, 12e9 // (vec_len * 8))))  # at most ~12 GB of pinned host vectors
+    if args.e2e_snapshots:
+        n_e2e = max(2, min(n_e2e, args.e2e_snapshots))
     e2e_steps = max(1, min(steps, 10 if headline else 3))
     if os.environ.get("VASP_B200_E2E_BATCH"):  # experiments: snapshots per host->device batch (default: auto)
         eng.set_tuning(batch_snapshots=int(os.environ["VASP_B200_E2E_BATCH"]))
@@ -695,6 +697,7 @@ def main() -> None:
     ap.add_argument("--no-other-workloads", action="store_true",
                     help="measure the headline workload only (default: BASELINE configs[2..4] ride in the same line)")
     ap.add_argument("--other-steps", type=int, default=5, help="timed steps per non-headline workload")
+    ap.add_argument("--e2e-snapshots", type=int, default=0, help="bound of the end-to-end sample (host vectors per GPU)")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
                     help="weak: every GPU processes --snapshots; strong: --snapshots are split over the GPUs")
     ap.add_argument("--no-parity", dest="parity", action="store_false",

@@ -137,30 +137,6 @@ void gather_range(const double* __restrict__ src, const int32_t* __restrict__ sl
     double* o1 = out + ld;
     double* o2 = out + 2 * ld;
     const bool interleaved = off[1] == off[0] + 1 && off[2] == off[0] + 2;  // one line serves the three components
-    static const int scramble = [] {
-        const char* e = getenv("VASP_B200_GATHER_ORDER");
-        return e && *e ? atoi(e) : 0;
-    }();
-    if (scramble && i1 - i0 == GATHER_NODES) {
-        // experiment: visit the nodes of the chunk in a scrambled order (odd multiplier modulo 2^14) so that the
-        // hardware stream prefetchers do not pull in the lines between wall-layer nodes
-        constexpr int64_t M = 6151, MASK = GATHER_NODES - 1;
-        for (int64_t j = 0; j < GATHER_NODES; ++j) {
-            const int64_t ip = i0 + (((j + PREFETCH_AHEAD) * M) & MASK);
-            const int64_t sp = slot[ip];
-            __builtin_prefetch(s0 + sp, 0, 0);
-            if (!interleaved) {
-                __builtin_prefetch(s1 + sp, 0, 0);
-                __builtin_prefetch(s2 + sp, 0, 0);
-            }
-            const int64_t i = i0 + ((j * M) & MASK);
-            const int64_t sl = slot[i];
-            o0[i] = s0[sl];
-            o1[i] = s1[sl];
-            o2[i] = s2[sl];
-        }
-        return;
-    }
     const int64_t ipf = i1 - PREFETCH_AHEAD;
     int64_t i = i0;
     for (; i < ipf; ++i) {
@@ -192,13 +168,16 @@ bool compact_wanted(const vh_handle* h) {
     // cores at ~10 GB/s per thread up to ~160 GB/s (it touches nearly every cache line once the wall layer is more than
     // a few per cent of the nodes), the plain copy moves every byte at 54 GB/s over PCIe.  With >= 6 threads the
     // gather wins up to a wall-layer share of about a third (1.5x at 20 %, 2.7x at 7 %); at 72 % (the tutorial-size
-    // mesh) it loses.  With fewer threads only a very thin wall layer pays.
+    // mesh) it loses.  With 3-5 threads (eight ranks on a 32-core host) it breaks even below ~12 % (+4 % at 7 %, -9 % at
+    // 9 %, -36 % at 20 %) -- and is still taken there, because on the device the staging kernel is then a transpose at
+    // the HBM peak instead of a sector-bound gather (5x less K1 time on the 10 M-tet mesh).  With fewer threads only a
+    // very thin wall layer pays.
     static const double limit_env = [] {
         const char* e = getenv("VASP_B200_COMPACT_RATIO");
         return e && *e ? atof(e) : -1.0;
     }();
     const int threads = h->host_threads > 0 ? h->host_threads : auto_threads();
-    const double limit = limit_env >= 0.0 ? limit_env : (threads >= 6 ? 0.35 : 0.05);
+    const double limit = limit_env >= 0.0 ? limit_env : (threads >= 6 ? 0.35 : threads >= 3 ? 0.12 : 0.05);
     const double slots = (double)((h->vec_len + 2) / 3);
     return slots > 0 && (double)h->nWn_pad <= limit * slots;
 }
