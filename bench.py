@@ -582,7 +582,7 @@ def io_leg(wl, n_snap: int, u_host: np.ndarray, device: int, io_bytes: int = 1 <
     import io as _io
 
     order, vec_len = wl["order"], u_host.shape[1]
-    n_io = int(max(3, min(n_snap, io_bytes // (vec_len * 8))))
+    n_io = int(max(3, min(n_snap, io_bytes // (vec_len * 8), len(u_host) - wl["halo"])))
     tmp = Path(tempfile.mkdtemp(prefix="vasp_b200_io_"))
     try:
         (tmp / "Mesh").mkdir()
@@ -611,7 +611,7 @@ def io_leg(wl, n_snap: int, u_host: np.ndarray, device: int, io_bytes: int = 1 <
         eng = HemoEngine(device)
         eng.set_mesh(wl["xyz"], wl["tets"])
         eng.set_velocity_layout(order, refined_xyz=wl["points"] if order == 2 else None)
-        block = default_block_snapshots(vec_len, eng.compact_len if eng.compaction_active else 0)
+        block = default_block_snapshots(vec_len, eng.compact_len if eng.compaction_active else 0, eng.nF)
         eng.set_tuning(batch_snapshots=block, chunk_snapshots=0)
 
         def run_once():

@@ -150,8 +150,10 @@ def test_series_reads_in_pieces_over_a_thread_pool(tmp_path, monkeypatch):
         got.append(np.array(u[:, :3 * n]))
     assert np.array_equal(np.concatenate(got), vecs[2:])
     assert default_block_snapshots(3 * 2997) == 116 and default_block_snapshots(3 * 13_400_000) == 2
-    # compact rows (wall layer gathered on the way): up to 64 snapshots within 1 GiB, so that a block fills K2's lanes
-    assert default_block_snapshots(3 * 13_400_000, 3 * 998_688) == 44 and default_block_snapshots(3 * 351_329, 3 * 70_688) == 64
+    # ~8 MiB of the larger of what is read (compact rows when the wall layer is gathered on the way) and of the WSS block
+    assert default_block_snapshots(3 * 2997, 0, 2560) == 45
+    assert default_block_snapshots(3 * 13_400_000, 3 * 998_688, 224_768) == 2
+    assert default_block_snapshots(3 * 351_329, 3 * 70_688) == 4 and default_block_snapshots(3 * 351_329, 3 * 70_688, 72_960) == 2
     s.close()
 
 

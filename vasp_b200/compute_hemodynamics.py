@@ -127,17 +127,16 @@ class _Drain:
         self._check()
 
 
-def default_block_snapshots(vec_len: int, compact_len: int = 0) -> int:
-    """Snapshots per pinned read buffer: ~8 MiB, at least 2 and at most 512.  Small blocks matter twice: nothing
-    overlaps the first block's read, and pinning memory costs about as much per byte as reading it (measured:
-    2 x 260 MB buffers cost more than reading the 1 GB file from the page cache, profiles/r1io_*).  When the wall layer
-    is gathered on the way (``compact_len`` doubles per snapshot land in the buffer instead of ``vec_len``) the rows
-    are small, and a block should also fill the lanes of the traction kernel: up to 64 snapshots within 1 GiB."""
-    row = (compact_len or vec_len) * 8
-    n = (8 << 20) // row
-    if compact_len:
-        n = max(n, min(64, (1 << 30) // row))
-    return int(min(512, max(2, n)))
+def default_block_snapshots(vec_len: int, compact_len: int = 0, n_facets: int = 0) -> int:
+    """Snapshots per pinned buffer: ~8 MiB of whichever is larger per snapshot -- what lands in the read buffer
+    (``compact_len`` doubles when the wall layer is gathered on the way, else the whole vector) or the WSS block that
+    comes back (72 bytes per facet) -- at least 2 and at most 512.  Small blocks matter twice: nothing overlaps the
+    first block's read, and pinning memory costs about as much per byte as reading it (measured: 2 x 260 MB buffers
+    cost more than reading the 1 GB file from the page cache, profiles/r1io_*; 64-snapshot blocks of compact rows made
+    the 2 M-tet entry point 0.17 s slower than 9-snapshot ones, profiles/r2h_*).  The kernels do not care: a push of a
+    few columns costs what one 64-column pass costs, far less than reading those snapshots."""
+    row = max((compact_len or vec_len) * 8, 72 * n_facets)
+    return int(min(512, max(2, (8 << 20) // row)))
 
 
 class _BlockReader:
@@ -296,7 +295,7 @@ def compute_hemodyanamics(visualization_separate_domain_folder: Path, mesh_path:
     nF = eng.nF
     compacting = eng.compaction_active and hasattr(series, "row_addresses")
     if block_snapshots is None:
-        block_snapshots = default_block_snapshots(series.vec_len, eng.compact_len if compacting else 0)
+        block_snapshots = default_block_snapshots(series.vec_len, eng.compact_len if compacting else 0, nF)
         if wss_matrix_folder is not None:
             # the matrix comes back as a pitched copy of 9 nF rows of (block x 8) bytes: keep the rows >= 256 bytes
             # unless that would pin more than 1 GiB per read buffer
