@@ -273,3 +273,18 @@ def test_rank_and_world_from_mpi_and_slurm_launchers(monkeypatch):
     monkeypatch.setenv("WORLD_SIZE", "4")
     monkeypatch.setenv("LOCAL_RANK", "0")
     assert timeshard.env_rank_world() == (0, 0, 4)            # torchrun's contract first
+
+
+def test_bench_series_is_one_series_whatever_the_sharding():
+    """bench.py: every rank synthesises its own snapshots of ONE long series (weak: rank r owns [r n, (r + 1) n) plus a
+    halo; strong: plan_shard ranges), and rank 0 re-synthesises the whole of it for the parity check -- the pieces must
+    be the series, bit for bit."""
+    import bench
+    whole, dt = bench.series_coefficients(37, 0, 20)
+    for first, n in ((0, 9), (8, 11), (19, 18)):
+        part, dt_p = bench.series_coefficients(n, first, 20)
+        assert dt_p == dt and np.array_equal(part, whole[first:first + n])
+    sh = [timeshard.plan_shard(37, r, 4) for r in range(4)]
+    assert [s.start for s in sh] == [0, 10, 19, 28] and sh[-1].stop == 37
+    assert bench.algorithmic_bytes_per_unit(2) == 240 and bench.algorithmic_bytes_per_unit(1, True) == 168   # SURVEY §8d
+    assert set(bench.OTHER_WORKLOADS) <= set(bench.WORKLOADS) and all(r >= 256 for r, _ in bench.OTHER_WORKLOADS.values())
