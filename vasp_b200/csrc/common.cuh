@@ -150,7 +150,7 @@ struct vh_handle {
     uint64_t peer_epoch = 0;
     // programmatic stream serialization per kernel: bit 0 K1, bit 1 K2, bit 2 K3 (VASP_B200_PDL).  Measured (profiles/
     // r1pdl): K1 + K2 is the best mask (55.8 us per headline step against 64 without); adding K3 costs 30 us on P2.
-    int pdl = 11;                  // bit 3: the fused peer reduction after K3 (2 GPUs, headline: 72.4 -> 70.3 us per step)
+    int pdl = 3;                   // (the fused peer reduction used to be bit 3; it now runs on its own stream, s_aux)
     bool k2_configured[8] = {false, false, false, false, false, false, false, false};  // cudaFuncSetAttribute done on this handle's device, per (order, launch shape)
     bool peer_unchecked = false;   // a fused reduction was enqueued and its "peer lost" word not looked at yet
     // The fused reduction runs on s_aux behind the K3 of its time loop, so the next loop's K1/K2 overlap the cross-GPU
