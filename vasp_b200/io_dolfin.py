@@ -28,8 +28,8 @@ from .h5lite import H5File, H5FormatError, H5Writer, dataset_table
 def read_mesh(path: Union[str, Path], group: str = "mesh") -> Tuple[np.ndarray, np.ndarray]:
     """``(coordinates (nv,3) f8, topology (nc,4) i8)``; file row order is the cell numbering."""
     with H5File(path) as f:
-        xyz = f[f"{group}/coordinates"].read().astype(np.float64)
-        tets = f[f"{group}/topology"].read().astype(np.int64)
+        xyz = f[f"{group}/coordinates"].read().astype(np.float64, copy=False)   # read() already is a private copy
+        tets = f[f"{group}/topology"].read().astype(np.int64, copy=False)
     if xyz.ndim != 2 or xyz.shape[1] != 3 or tets.ndim != 2 or tets.shape[1] != 4:
         raise ValueError(f"{path}: expected a tetrahedral mesh in 3-D")
     return xyz, tets
