@@ -213,3 +213,31 @@ def test_quadrature_rules_are_what_they_claim():
     for i, j, k in ((0, 0, 0), (1, 0, 0), (0, 1, 0), (2, 0, 0), (1, 1, 0), (0, 1, 1), (0, 0, 2)):
         exact = 2 * math.factorial(i) * math.factorial(j) * math.factorial(k) / math.factorial(i + j + k + 2)
         assert abs(np.sum(q2w * q2p[:, 0] ** i * q2p[:, 1] ** j * q2p[:, 2] ** k) - exact) < 1e-15
+
+
+@pytest.mark.parametrize("name", ["cylinder", "stenosis", "aneurysm"])
+def test_boundary_mesh_is_ordered_like_boundarymesh_with_default_order(name):
+    """``BoundaryMesh(mesh, "exterior")`` (compute_hemodynamics.py:191) leaves ``order`` at dolfin's default ``True``:
+    after ``BoundaryComputation`` has numbered the boundary vertices by first encounter over the exterior facets (in facet
+    order, vertices ascending), ``Mesh.order()`` sorts every boundary cell's vertices ascending in BOUNDARY vertex number
+    [dolfin-recall; ADVICE r1].  The maps the CUDA precompute must reproduce bit-exactly have exactly that structure."""
+    src = H.load_fluid(name)
+    S = ho.SurfaceStress(src["xyz"], src["tets"], 1.0, 1)
+    m = S.maps
+    assert np.all(np.diff(m.btopology, axis=1) > 0)                                   # cells ordered
+    assert np.array_equal(m.bvert_parent[m.btopology], m.bcell_parent)                # same cells, parent numbering
+    assert np.array_equal(np.sort(m.bcell_parent, axis=1), m.facets)                  # the facet's three vertices
+    seen, order = set(), []
+    for v in m.facets.reshape(-1):                                                    # first encounter, facet by facet
+        if v not in seen:
+            seen.add(v)
+            order.append(v)
+    assert np.array_equal(m.bvert_parent, np.array(order))
+    # the dof copy (InterpolateDG) follows the cell order: boundary dof j of cell i sits on vertex bcell_parent[i, j]
+    tets = ho.order_cells(src["tets"])
+    assert np.array_equal(tets[m.facet_cell[:, None], m.bcell_local.astype(np.int64)], m.bcell_parent)
+    # on these meshes the ordered cells are NOT all right-oriented (that would be order=False)
+    p = src["xyz"][m.bcell_parent]
+    nrm = np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0])
+    out = np.einsum("ij,ij->i", nrm, S.normal)
+    assert (out > 0).any() and (out < 0).any()
