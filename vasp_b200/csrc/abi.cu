@@ -23,6 +23,10 @@ namespace {
 
 inline void nvtx_push(const char* name) { nvtxRangePushA(name); }
 inline void nvtx_pop() { nvtxRangePop(); }
+struct NvtxRange {  // a named range over a scope (shows up in nsys / ncu --nvtx)
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct NcclApi {
     void* lib = nullptr;
@@ -371,6 +375,7 @@ static int prev_mode_for(vh_handle* h, int flags, const char* who, int* mode) {
 // Device-resident snapshots: whole vectors (K1 gathers the wall layer) or compact blocks (K1 transposes).
 static int push_device(vh_handle* h, const char* who, const double* d_u, int64_t n_snap, int64_t stride_bytes, int flags,
                        double* d_wss_out, bool dense) {
+    NvtxRange range(dense ? "push resident compact blocks (K1 transpose, K2, K3)" : "push resident vectors (K1 gather, K2, K3)");
     VH_TRY(check_ready(h, who));
     VH_CHECK(d_u && n_snap > 0, VH_ERR_ARG, "%s: nothing to push", who);
     const int64_t row_elems = dense ? 3 * h->nWn_pad : h->vec_len;
@@ -411,6 +416,8 @@ enum { SRC_FULL = 0, SRC_GATHER = 1, SRC_COMPACT = 2 };
 
 static int push_host(vh_handle* h, const char* who, const double* u, int64_t n_snap, int64_t stride_bytes, int flags,
                      double* wss_out, int kind) {
+    NvtxRange range(kind == SRC_GATHER ? "push host vectors (host gather, H2D, K1-K3)"
+                    : kind == SRC_COMPACT ? "push host compact blocks (H2D, K1-K3)" : "push host vectors (H2D, K1-K3)");
     VH_TRY(check_ready(h, who));
     VH_CHECK(u && n_snap > 0, VH_ERR_ARG, "%s: nothing to push", who);
     const bool dense = kind != SRC_FULL;
@@ -707,6 +714,7 @@ int vh_get_tau_last(vh_handle* h, double* tau) {
 }
 
 int vh_finalize(vh_handle* h, int64_t n_total, double* tawss, double* osi, double* rrt, double* ecap, double* twssg) {
+    NvtxRange range("finalize (indices, D2H)");
     VH_TRY(check_ready(h, "vh_finalize"));
     VH_CHECK(n_total > 0, VH_ERR_ARG, "vh_finalize: n_total must be positive");
     VH_TRY(settle_sums(h));
@@ -1011,6 +1019,7 @@ int vh_peer_init(vh_handle* h) {
 
 int vh_peer_reduce_finalize(vh_handle* h, int64_t n_total, double* tawss, double* osi, double* rrt, double* ecap,
                             double* twssg) {
+    NvtxRange range("fused cross-GPU reduction + indices");
     VH_TRY(check_ready(h, "vh_peer_reduce_finalize"));
     VH_CHECK(h->peer_ready, VH_ERR_ARG, "vh_peer_reduce_finalize: call vh_peer_init first");
     VH_CHECK(n_total > 0, VH_ERR_ARG, "vh_peer_reduce_finalize: n_total must be positive");
