@@ -288,3 +288,26 @@ def test_bench_series_is_one_series_whatever_the_sharding():
     assert [s.start for s in sh] == [0, 10, 19, 28] and sh[-1].stop == 37
     assert bench.algorithmic_bytes_per_unit(2) == 240 and bench.algorithmic_bytes_per_unit(1, True) == 168
     assert set(bench.OTHER_WORKLOADS) <= set(bench.WORKLOADS) and all(r >= 256 for r, _ in bench.OTHER_WORKLOADS.values())
+
+
+def test_reference_arm_of_the_bench_prints_the_contract_line():
+    """``bench.py --impl reference`` (the CPU arm the driver runs beside ours: the C twin of the oracle on the host cores,
+    a bounded sample of the same workload) prints ONE JSON line with the keys of the bench contract; under a launcher
+    only rank 0 prints."""
+    import subprocess
+    import sys
+    env = {k: v for k, v in __import__("os").environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--snapshots", "64"]
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "wall_facet_snapshots_per_s" and d["higher_is_better"] is True
+    assert d["unit"] == "facet*snapshots/s" and d["value"] > 0 and d["n_gpus"] == 1 and d["dtype"] == "f64"
+    assert d["config"]["workload"].startswith("stenosis_p1") and d["config"]["facets"] == 2560
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "snapshots" in d["cpu_baseline"]["sample"]
+    rank1 = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=300,
+                           env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
+    assert rank1.returncode == 0 and not [ln for ln in rank1.stdout.splitlines() if ln.startswith("{")]
