@@ -39,6 +39,7 @@ def test_baseline_p2_meshes_against_the_oracle(engine_lib, name, n_long):
     eng = HemoEngine(0)
     eng.set_mesh(g["xyz"], g["tets"])
     eng.set_velocity_layout(2, refined_xyz=g["points"])
+    eng.set_host_compaction("auto", 8)   # the automatic rule looks at the thread count; do not depend on the box's cores
     m, S = eng.maps(), stress.maps
     assert len(g["tets"]) > (9.9e6 if name == "vessel10m_p2" else 4.9e6)
     for key, want in (("facets", S.facets), ("facet_cell", S.facet_cell), ("facet_local", S.facet_local),
@@ -57,7 +58,7 @@ def test_baseline_p2_meshes_against_the_oracle(engine_lib, name, n_long):
     want_sums = np.concatenate([res["wss_sum"].reshape(-1, 9).T, res["tawss_sum"].T, res["twssg_sum"].T])
     got = {}
     for mode in ("off", "on"):
-        eng.set_host_compaction(mode)
+        eng.set_host_compaction(mode, 8)
         eng.begin(bench.MU, dt)
         eng.push(u, flags=1)
         sums, cnt = eng.sums()

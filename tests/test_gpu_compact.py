@@ -14,7 +14,7 @@ TOL = 1e-10
 
 
 def _run(eng, case, mu, mode, u=None, flags=1, keep_wss=False):
-    eng.set_host_compaction(mode)
+    eng.set_host_compaction(mode, 8)   # 8 gather threads whatever the box has: the automatic rule looks at the count
     eng.begin(mu, case["dt"])
     wss = eng.push(case["u"] if u is None else u, flags=flags, keep_wss=keep_wss)
     sums, cnt = eng.sums()
@@ -69,7 +69,7 @@ def test_compact_route_is_bitwise_the_whole_vector_route(engine_lib, name, order
     eng.push_compact_device(d + 29 * cu.strides[0], 71 - 29, cu.strides[0], flags=2)  # snapshot 29 is the halo
     s_halo, c_halo = eng.sums()
     eng.begin(mu, case["dt"])
-    eng.set_host_compaction("off")
+    eng.set_host_compaction("off", 8)
     eng.push(case["u"][29:], flags=2)
     s_halo_ref, c_ref = eng.sums()
     # one launch over the resident block against the batches of a host push: summation order only
@@ -96,7 +96,7 @@ def test_compaction_with_interleaved_layout_and_injected_node_perm(engine_lib):
         eng = HemoEngine(0)
         eng.set_mesh(case["xyz"], case["tets"])
         eng.set_velocity_layout(2, refined_xyz=case["points"], node_perm=ids, comp_offset=(0, 1, 2), node_stride=3)
-        eng.set_host_compaction(mode)
+        eng.set_host_compaction(mode, 4)
         eng.begin(mu, case["dt"])
         wss = np.array(eng.push(raw, flags=1, keep_wss=True))
         outs[mode] = (eng.sums()[0], wss, eng.finalize())
@@ -116,6 +116,7 @@ def test_auto_mode_compacts_large_meshes_and_batches_split(engine_lib):
     case = H.make_case(mesh["xyz"], mesh["tets"], 1, n_snap=150, seed=11)
     mu = 3.5e-3
     eng = H.engine_for(case, mu)
+    eng.set_host_compaction("auto", 8)
     assert eng.compaction_active and eng.n_wall_nodes < 0.35 * eng.n_nodes
     s_auto, _, f_auto, _, _ = _run(eng, case, mu, "auto")
     assert eng.io_stats()["h2d_bytes"] == 150 * 8 * eng.compact_len
